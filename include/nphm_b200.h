@@ -1,0 +1,175 @@
+/* nphm_b200.h - C ABI of libnphm_b200.so, the B200-native engine behind NPHM's hot path.
+ *
+ * The reference (SimonGiebenhain/NPHM) has no FFI layer: its hot path sits behind Python call signatures
+ * (SURVEY.md 8b).  This header is the boundary a binding would target; the Python mirror of the reference
+ * modules in nphm_b200/ binds it with ctypes (nphm_b200/_native.py), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns NPHM_OK (0) or a negative error code; nphm_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - pointers named *_dev are CUDA device pointers on the current device, *_host are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on that
+ *     stream unless stated otherwise.  No torch types appear in any signature.
+ *   - all network arithmetic is fp32 in / fp32 out; weights are given in the reference's state_dict layout.
+ *   - handles are not thread safe; use one handle per host thread / stream.
+ */
+#ifndef NPHM_B200_H
+#define NPHM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPHM_OK               0
+#define NPHM_ERR_INVALID     -1   /* bad argument */
+#define NPHM_ERR_CUDA        -2   /* a CUDA runtime call failed */
+#define NPHM_ERR_UNSUPPORTED -3   /* configuration not supported by the requested kernel */
+#define NPHM_ERR_CAPACITY    -4   /* caller-provided buffer too small */
+
+/* kernel selection for the network queries */
+#define NPHM_IMPL_AUTO   0   /* tcgen05 kernel when the configuration allows it, else SIMT */
+#define NPHM_IMPL_SIMT   1   /* fp32 FFMA kernel (any configuration) */
+#define NPHM_IMPL_TC     2   /* tcgen05 / TMEM kernel, 3-pass fp16 split (fp32-equivalent accuracy) */
+
+const char *nphm_last_error(void);
+int nphm_abi_version(void);
+/* sm count and compute capability of the current device */
+int nphm_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Identity SDF ensemble  == FastEnsembleDeepSDFMirrored (reference src/NPHM/models/EnsembledDeepSDF.py:153-267)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nphm_ensemble nphm_ensemble;
+
+typedef struct {
+    int n_loc;          /* facial anchors (39); ensemble size is n_loc + 1              (:183)      */
+    int n_symm_pairs;   /* mirrored anchor pairs sharing weights (16)                   (:184,:43)  */
+    int lat_dim_glob;   /* 64                                                                        */
+    int lat_dim_loc;    /* 32; latent = [z_glob, z_0 .. z_{n_loc-1}, z_global_member]   (:210-212)  */
+    int hidden_dim;     /* 200                                                                       */
+    int n_layers;       /* 4 hidden layers -> 5 linear layers, skip at n_layers/2       (:80-96)    */
+    int pos_mlp_dim;    /* hidden width of mlp_pos (256)                                (:194-200)  */
+} nphm_ensemble_config;
+
+int nphm_ensemble_create(const nphm_ensemble_config *cfg, nphm_ensemble **out);
+void nphm_ensemble_destroy(nphm_ensemble *h);
+
+/* Replaces `load_state_dict` for the engine.  lin_w_dev[l]: (n_sets, out_l, in_l) row-major, lin_b_dev[l]:
+ * (n_sets, out_l) for l = 0..n_layers (keys ensembled_deep_sdf.lin{l}.weight/bias, n_sets = n_loc+1-n_symm_pairs);
+ * pos_w_dev/pos_b_dev: the three nn.Linear of mlp_pos (keys mlp_pos.{0,2,4}); mean_anchors_dev: n_loc*3.
+ * Packs/splits the weights for every kernel; must be called again after the parameters change. */
+int nphm_ensemble_load_weights(nphm_ensemble *h,
+                               const float *const *lin_w_dev, const float *const *lin_b_dev,
+                               const float *const *pos_w_dev, const float *const *pos_b_dev,
+                               const float *mean_anchors_dev, void *stream);
+
+/* == FastEnsembleDeepSDFMirrored.forward(xyz, lat_rep, None) for lat_rep constant over the points of a query.
+ *   xyz_dev       n_queries * n_points * 3
+ *   latents_dev   n_queries * lat_dim
+ *   quirk_period  eval-mode quirk of :260-261 (`sdf_pred[:, :, -1, 0] = 1` hits the LAST POINT of a call):
+ *                 0 = train mode (off); p > 0 = points with (i % p == p-1) or i == n_points-1 get s_k = 1 for all
+ *                 members.  A plain forward call uses p = n_points; get_logits (models/reconstruction.py:13) uses
+ *                 p = nbatch_points.
+ *   out_sdf_dev   n_queries * n_points           out_anchors_dev  n_queries * n_loc * 3 (may be NULL)        */
+int nphm_ensemble_query(nphm_ensemble *h, const float *xyz_dev, const float *latents_dev,
+                        int n_queries, long long n_points, long long quirk_period,
+                        float *out_sdf_dev, float *out_anchors_dev, int impl, void *stream);
+
+/* Same for ONE latent over (a contiguous range of) the regular grid of
+ * create_grid_points_from_bounds (utils/reconstruction.py:5-20): point g = first + i, i < count, has
+ * (ix,iy,iz) = unravel(g, res^3), z fastest, coordinates float32(linspace_f64(min,max,res)[i*]).  The points are
+ * generated in the kernel (no xyz traffic).  The quirk uses the GLOBAL index g, so shards agree with a
+ * single-GPU run.  out_sdf_dev: count floats. */
+int nphm_ensemble_query_grid(nphm_ensemble *h, const float *latent_dev,
+                             const double grid_min[3], const double grid_max[3], int res,
+                             long long first, long long count, long long quirk_period,
+                             float *out_sdf_dev, float *out_anchors_dev, int impl, void *stream);
+
+/* Host-buffer convenience used for end-to-end timing: latent_host (lat_dim floats) -> device, grid query of the
+ * whole res^3 grid, volume -> out_host (res^3 floats).  Synchronous. */
+int nphm_ensemble_get_logits_host(nphm_ensemble *h, const float *latent_host,
+                                  const double grid_min[3], const double grid_max[3], int res,
+                                  long long quirk_period, float *out_host, int impl);
+
+/* ------------------------------------------------------------------------------------------------
+ * Plain DeepSDF MLP == DeepSDF.forward (reference src/NPHM/models/deepSDF.py:6-89), also the backbone of
+ * DeformationNetwork (:118-239) whose condition vector the host builds (compressor Linear, :218-223).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nphm_mlp nphm_mlp;
+
+typedef struct {
+    int lat_dim;      /* condition width (232 for the deformation backbone)  */
+    int hidden_dim;   /* 512                                                 */
+    int n_layers;     /* hidden layers (6) -> n_layers+1 linear, skip at n_layers/2 */
+    int out_dim;      /* 3                                                   */
+} nphm_mlp_config;
+
+int nphm_mlp_create(const nphm_mlp_config *cfg, nphm_mlp **out);
+void nphm_mlp_destroy(nphm_mlp *h);
+/* w_dev[l]: (out_l, in_l) row-major, b_dev[l]: (out_l), l = 0..n_layers (keys lin{l}.weight/bias). */
+int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, const float *const *b_dev, void *stream);
+/* xyz_dev n_queries*n_points*3, cond_dev n_queries*lat_dim -> out_dev n_queries*n_points*out_dim */
+int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries,
+                   long long n_points, float *out_dev, int impl, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Marching cubes == mcubes.marching_cubes(volume, iso) as called at utils/reconstruction.py:30
+ * (PyMCubes semantics restated in oracle/mc_oracle.c: x-major cell order, `<=` classification, one vertex per
+ * crossed grid edge numbered in creation order, double-precision interpolation, classic 256-case table).
+ * The volume is a slab of nx planes (x slowest, z fastest) that may be a shard of a larger grid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int nx, ny, nz;       /* planes / rows / columns of vol_dev                                               */
+    int x_global0;        /* global x index of plane 0 (0 for a whole volume)                                 */
+    int ghost_lo;         /* 1: the first cell layer belongs to the previous shard; it is classified so that
+                             shared vertices resolve to the right ids, but emits nothing                      */
+    int negate;           /* 1: run on -vol (mesh_from_logits negates the SDF, utils/reconstruction.py:25)    */
+    double iso;
+} nphm_mc_params;
+
+/* bytes of scratch the two calls below need for this slab */
+long long nphm_mc_workspace_bytes(const nphm_mc_params *p);
+/* Pass 1: classify + count.  Writes the number of vertices / triangles this slab emits to the two host
+ * integers (synchronises the stream). */
+int nphm_mc_count(const float *vol_dev, const nphm_mc_params *p, void *workspace_dev,
+                  long long *n_verts_host, long long *n_tris_host, void *stream);
+/* Pass 2 (after nphm_mc_count on the same workspace): emit.  verts_dev: n_verts*3 doubles in GLOBAL index units;
+ * tris_dev: n_tris*3 int64 vertex ids offset by vert_id_base (the number of vertices emitted by all earlier
+ * shards; 0 for a whole volume). */
+int nphm_mc_emit(const float *vol_dev, const nphm_mc_params *p, void *workspace_dev,
+                 long long vert_id_base, double *verts_dev, long long *tris_dev, void *stream);
+/* Host-buffer convenience == mcubes.marching_cubes on a host volume: two-call protocol, call with
+ * verts_host == NULL to get the counts. Synchronous. */
+int nphm_marching_cubes_host(const float *vol_host, int nx, int ny, int nz, double iso, int negate,
+                             double *verts_host, long long *tris_host,
+                             long long *n_verts, long long *n_tris);
+
+/* ------------------------------------------------------------------------------------------------
+ * Identity-space fitting step == one iteration of inference_identity_space
+ * (reference src/NPHM/models/fitting.py:197-279): ensemble forward on the sampled observation points, clamped
+ * |sdf| loss, latent regularisers, analytic gradient w.r.t. the latent (through the member inputs, the
+ * anchors/mlp_pos and the blend weights), torch.optim.Adam update.  No autograd graph.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float lambda_surface, lambda_reg_global, lambda_reg_loc, lambda_reg_unobserved, lambda_symm_dist;
+    float clamp;          /* keep |sdf| < clamp (0.1 / 0.05 / 0.0075 by iteration, :239-246)                */
+    float lr;             /* current Adam lr                                                                 */
+    int   step;           /* 1-based Adam step count                                                         */
+} nphm_fit_params;
+
+/* bytes of scratch for n_points observation points */
+long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long n_points);
+/* latent_dev (lat_dim) is updated in place; adam_m_dev / adam_v_dev are the optimiser state (lat_dim each,
+ * zero-initialised by the caller).  loss_terms_dev (may be NULL) receives
+ * [surface, reg_global, reg_loc, reg_unobserved, symm_dist, n_kept].  grad_out_dev (may be NULL) receives the
+ * latent gradient (lat_dim). If `apply_update` is 0 only loss/gradient are produced. */
+int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev, long long n_points,
+                           float *latent_dev, float *adam_m_dev, float *adam_v_dev,
+                           const nphm_fit_params *fp, int apply_update,
+                           float *loss_terms_dev, float *grad_out_dev,
+                           void *workspace_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPHM_B200_H */

@@ -1,0 +1,381 @@
+"""ctypes binding of ``libnphm_b200.so`` (C ABI declared in ``include/nphm_b200.h``).
+
+PyTorch is used here only for device memory, streams and the caching allocator; the arithmetic of
+the hot path happens inside the library.  There is NO fallback: if the library is missing or a call
+fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_longlong,
+                    c_void_p)
+from typing import Optional
+
+import numpy as np
+import torch
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+_IMPL_BY_NAME = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC}
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libnphm_b200.so')
+_lib = None
+
+# every symbol include/nphm_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = (
+    'nphm_last_error', 'nphm_abi_version', 'nphm_device_info',
+    'nphm_ensemble_create', 'nphm_ensemble_destroy', 'nphm_ensemble_load_weights',
+    'nphm_ensemble_query', 'nphm_ensemble_query_grid', 'nphm_ensemble_get_logits_host',
+    'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
+    'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
+    'nphm_fit_workspace_bytes', 'nphm_fit_identity_step',
+)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class EnsembleConfig(Structure):
+    _fields_ = [('n_loc', c_int), ('n_symm_pairs', c_int), ('lat_dim_glob', c_int), ('lat_dim_loc', c_int),
+                ('hidden_dim', c_int), ('n_layers', c_int), ('pos_mlp_dim', c_int)]
+
+
+class MlpConfig(Structure):
+    _fields_ = [('lat_dim', c_int), ('hidden_dim', c_int), ('n_layers', c_int), ('out_dim', c_int)]
+
+
+class McParams(Structure):
+    _fields_ = [('nx', c_int), ('ny', c_int), ('nz', c_int), ('x_global0', c_int), ('ghost_lo', c_int),
+                ('negate', c_int), ('iso', c_double)]
+
+
+class FitParams(Structure):
+    _fields_ = [('lambda_surface', c_float), ('lambda_reg_global', c_float), ('lambda_reg_loc', c_float),
+                ('lambda_reg_unobserved', c_float), ('lambda_symm_dist', c_float), ('clamp', c_float),
+                ('lr', c_float), ('step', c_int)]
+
+
+def impl_code(impl) -> int:
+    if isinstance(impl, str):
+        return _IMPL_BY_NAME[impl]
+    return int(impl)
+
+
+def default_impl() -> int:
+    """Kernel selection for the drop-in modules; override with NPHM_B200_IMPL=auto|simt|tc."""
+    return _IMPL_BY_NAME[os.environ.get('NPHM_B200_IMPL', 'auto')]
+
+
+def lib() -> ctypes.CDLL:
+    """Load the native library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeError('%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(or `make -C nphm_b200/csrc`). The fused CUDA path has no fallback.' % _LIB_PATH)
+    L = ctypes.CDLL(_LIB_PATH)
+    L.nphm_last_error.restype = c_char_p
+    L.nphm_abi_version.restype = c_int
+    L.nphm_device_info.argtypes = [POINTER(c_int)] * 3
+    L.nphm_ensemble_create.argtypes = [POINTER(EnsembleConfig), POINTER(c_void_p)]
+    L.nphm_ensemble_destroy.argtypes = [c_void_p]
+    L.nphm_ensemble_destroy.restype = None
+    L.nphm_ensemble_load_weights.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                             POINTER(c_void_p), c_void_p, c_void_p]
+    L.nphm_ensemble_query.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p,
+                                      c_void_p, c_int, c_void_p]
+    L.nphm_ensemble_query_grid.argtypes = [c_void_p, c_void_p, POINTER(c_double), POINTER(c_double), c_int,
+                                           c_longlong, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_void_p]
+    L.nphm_ensemble_get_logits_host.argtypes = [c_void_p, c_void_p, POINTER(c_double), POINTER(c_double), c_int,
+                                                c_longlong, c_void_p, c_int]
+    L.nphm_mlp_create.argtypes = [POINTER(MlpConfig), POINTER(c_void_p)]
+    L.nphm_mlp_destroy.argtypes = [c_void_p]
+    L.nphm_mlp_destroy.restype = None
+    L.nphm_mlp_load_weights.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_void_p]
+    L.nphm_mlp_query.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_void_p]
+    L.nphm_mc_workspace_bytes.argtypes = [POINTER(McParams)]
+    L.nphm_mc_workspace_bytes.restype = c_longlong
+    L.nphm_mc_count.argtypes = [c_void_p, POINTER(McParams), c_void_p, POINTER(c_longlong), POINTER(c_longlong),
+                                c_void_p]
+    L.nphm_mc_emit.argtypes = [c_void_p, POINTER(McParams), c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
+    L.nphm_marching_cubes_host.argtypes = [c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                                           POINTER(c_longlong), POINTER(c_longlong)]
+    L.nphm_fit_workspace_bytes.argtypes = [c_void_p, c_longlong]
+    L.nphm_fit_workspace_bytes.restype = c_longlong
+    L.nphm_fit_identity_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                         POINTER(FitParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is c_int and name not in ('nphm_abi_version',):
+            pass
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = lib().nphm_last_error()
+        raise NativeError('%s failed (%d): %s' % (what or 'libnphm_b200 call', rc,
+                                                   msg.decode() if msg else 'unknown error'))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _ptr_array(tensors):
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def constant_latent_rows(lat_rep: torch.Tensor) -> Optional[torch.Tensor]:
+    """``B x N x D`` (or ``B x 1 x D``) latent -> ``B x D`` if it is the same for all points of a batch
+    entry, else ``None``.  Broadcast views (stride 0) are recognised without reading the data; a
+    materialised ``repeat`` costs one comparison pass."""
+    if lat_rep.dim() == 2:
+        return lat_rep.contiguous()
+    if lat_rep.shape[1] == 1 or lat_rep.stride(1) == 0:
+        return lat_rep[:, 0].contiguous()
+    first = lat_rep[:, :1]
+    if bool((lat_rep == first).all()):
+        return first[:, 0].contiguous()
+    return None
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+class _Versioned:
+    """Tracks parameter identity/version so that packed weights are rebuilt after in-place updates,
+    ``load_state_dict`` or ``.to(device)``."""
+
+    def _signature(self, params):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+
+
+class EnsembleEngine(_Versioned):
+    """Native handle for one ``FastEnsembleDeepSDFMirrored`` (packed weights live on its device)."""
+
+    def __init__(self, module):
+        self._h = c_void_p()
+        e = module.ensembled_deep_sdf
+        n_lin = e.num_layers - 1
+        cfg = EnsembleConfig(module.num_kps, module.num_symm_pairs, module.lat_dim_glob, module.lat_dim_loc,
+                             e.lin0.out_features, n_lin - 1, module.pos_mlp_dim)
+        check(lib().nphm_ensemble_create(byref(cfg), byref(self._h)), 'nphm_ensemble_create')
+        self.n_lin = n_lin
+        self.n_loc = module.num_kps
+        self.lat_dim = module.lat_dim
+        self._sig = None
+        self.device = None
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.nphm_ensemble_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _params(self, module):
+        e = module.ensembled_deep_sdf
+        ps = []
+        for i in range(self.n_lin):
+            lin = getattr(e, 'lin%d' % i)
+            ps += [lin.weight, lin.bias]
+        for i in (0, 2, 4):
+            ps += [module.mlp_pos[i].weight, module.mlp_pos[i].bias]
+        return ps
+
+    def refresh(self, module):
+        ps = self._params(module)
+        sig = self._signature(ps)
+        if sig == self._sig:
+            return
+        dev = ps[0].device
+        if dev.type != 'cuda':
+            raise NativeError('the fused ensemble needs the module on a CUDA device (got %s)' % dev)
+        with torch.cuda.device(dev):
+            tens = [_f32c(p) for p in ps]
+            lw = tens[0:2 * self.n_lin:2]
+            lb = tens[1:2 * self.n_lin:2]
+            pw = tens[2 * self.n_lin::2]
+            pb = tens[2 * self.n_lin + 1::2]
+            mean = _f32c(module.mean_anchors(dev)).reshape(-1)
+            check(lib().nphm_ensemble_load_weights(self._h, _ptr_array(lw), _ptr_array(lb), _ptr_array(pw),
+                                                   _ptr_array(pb), mean.data_ptr(), _stream_ptr(dev)),
+                  'nphm_ensemble_load_weights')
+            # the library copies on the current stream; keep the temporaries alive until it is done
+            torch.cuda.current_stream(dev).synchronize()
+        self._sig = sig
+        self.device = dev
+
+    # ---------------------------------------------------------------- queries
+    def query(self, xyz: torch.Tensor, latents: torch.Tensor, eval_quirk: bool, quirk_period: Optional[int] = None,
+              impl: Optional[int] = None):
+        """xyz B x N x 3, latents B x lat_dim -> (sdf B x N x 1, anchors B x n_loc x 3)."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        latents = _f32c(latents).to(dev)
+        sdf = torch.empty(B, N, 1, device=dev, dtype=torch.float32)
+        anchors = torch.empty(B, self.n_loc, 3, device=dev, dtype=torch.float32)
+        period = 0 if not eval_quirk else (N if quirk_period is None else int(quirk_period))
+        with torch.cuda.device(dev):
+            check(lib().nphm_ensemble_query(self._h, xyz.data_ptr(), latents.data_ptr(), B, N, period,
+                                            sdf.data_ptr(), anchors.data_ptr(),
+                                            default_impl() if impl is None else impl_code(impl), _stream_ptr(dev)),
+                  'nphm_ensemble_query')
+        return sdf, anchors
+
+    def query_grid(self, latent: torch.Tensor, mini, maxi, res: int, first: int, count: int, quirk_period: int,
+                   impl: Optional[int] = None, out: Optional[torch.Tensor] = None):
+        """One latent over grid points [first, first+count) of the res^3 grid -> (sdf (count,), anchors)."""
+        dev = latent.device
+        latent = _f32c(latent).reshape(-1)
+        if out is None:
+            out = torch.empty(count, device=dev, dtype=torch.float32)
+        anchors = torch.empty(self.n_loc, 3, device=dev, dtype=torch.float32)
+        gmin = (c_double * 3)(*[float(v) for v in mini])
+        gmax = (c_double * 3)(*[float(v) for v in maxi])
+        with torch.cuda.device(dev):
+            check(lib().nphm_ensemble_query_grid(self._h, latent.data_ptr(), gmin, gmax, int(res), int(first),
+                                                 int(count), int(quirk_period), out.data_ptr(), anchors.data_ptr(),
+                                                 default_impl() if impl is None else impl_code(impl),
+                                                 _stream_ptr(dev)),
+                  'nphm_ensemble_query_grid')
+        return out, anchors
+
+
+class MlpEngine(_Versioned):
+    """Native handle for one ``DeepSDF`` stack (also the backbone of ``DeformationNetwork``)."""
+
+    def __init__(self, module):
+        self._h = c_void_p()
+        self.n_lin = module.num_layers - 1
+        cfg = MlpConfig(module.lat_dim, module.lin0.out_features, self.n_lin - 1, module.out_dim_net)
+        check(lib().nphm_mlp_create(byref(cfg), byref(self._h)), 'nphm_mlp_create')
+        self.out_dim = module.out_dim_net
+        self._sig = None
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.nphm_mlp_destroy(self._h)
+        except Exception:
+            pass
+
+    def refresh(self, module):
+        ps = []
+        for i in range(self.n_lin):
+            lin = getattr(module, 'lin%d' % i)
+            ps += [lin.weight, lin.bias]
+        sig = self._signature(ps)
+        if sig == self._sig:
+            return
+        dev = ps[0].device
+        if dev.type != 'cuda':
+            raise NativeError('the fused MLP needs the module on a CUDA device (got %s)' % dev)
+        with torch.cuda.device(dev):
+            tens = [_f32c(p) for p in ps]
+            check(lib().nphm_mlp_load_weights(self._h, _ptr_array(tens[0::2]), _ptr_array(tens[1::2]),
+                                              _stream_ptr(dev)), 'nphm_mlp_load_weights')
+            torch.cuda.current_stream(dev).synchronize()
+        self._sig = sig
+
+    def query(self, xyz: torch.Tensor, cond: torch.Tensor, impl: Optional[int] = None) -> torch.Tensor:
+        """xyz B x N x 3, cond B x lat_dim -> B x N x out_dim."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        cond = _f32c(cond).to(dev)
+        out = torch.empty(B, N, self.out_dim, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_mlp_query(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(),
+                                       IMPL_AUTO if impl is None else impl_code(impl), _stream_ptr(dev)),
+                  'nphm_mlp_query')
+        return out
+
+
+# ------------------------------------------------------------------------------------------ marching cubes
+def marching_cubes_device(volume: torch.Tensor, iso: float = 0.0, negate: bool = False, x_global0: int = 0,
+                          ghost_lo: bool = False, vert_id_base: Optional[int] = None):
+    """GPU marching cubes on a CUDA float32 volume (nx, ny, nz).  Returns (verts (V,3) float64 CUDA in global
+    index units, tris (T,3) int64 CUDA).  With ``vert_id_base=None`` ids start at 0; a sharded caller passes the
+    number of vertices of all earlier slabs, see ``nphm_b200.distributed``."""
+    assert volume.is_cuda and volume.dtype == torch.float32 and volume.dim() == 3
+    vol = volume.contiguous()
+    dev = vol.device
+    p = McParams(vol.shape[0], vol.shape[1], vol.shape[2], int(x_global0), int(bool(ghost_lo)), int(bool(negate)),
+                 float(iso))
+    L = lib()
+    ws_bytes = L.nphm_mc_workspace_bytes(byref(p))
+    if ws_bytes < 0:
+        check(-1, 'nphm_mc_workspace_bytes')
+    ws = torch.empty(max(int(ws_bytes), 256), device=dev, dtype=torch.uint8)
+    nv, nt = c_longlong(0), c_longlong(0)
+    with torch.cuda.device(dev):
+        check(L.nphm_mc_count(vol.data_ptr(), byref(p), ws.data_ptr(), byref(nv), byref(nt), _stream_ptr(dev)),
+              'nphm_mc_count')
+        verts = torch.empty(nv.value, 3, device=dev, dtype=torch.float64)
+        tris = torch.empty(nt.value, 3, device=dev, dtype=torch.int64)
+        if nv.value or nt.value:
+            check(L.nphm_mc_emit(vol.data_ptr(), byref(p), ws.data_ptr(), int(vert_id_base or 0),
+                                 verts.data_ptr(), tris.data_ptr(), _stream_ptr(dev)), 'nphm_mc_emit')
+    return verts, tris
+
+
+def marching_cubes_count(volume: torch.Tensor, iso=0.0, negate=False, x_global0=0, ghost_lo=False):
+    """Pass 1 only: (n_verts, n_tris, params, workspace) for a slab; used by the sharded extraction."""
+    vol = volume.contiguous()
+    dev = vol.device
+    p = McParams(vol.shape[0], vol.shape[1], vol.shape[2], int(x_global0), int(bool(ghost_lo)), int(bool(negate)),
+                 float(iso))
+    L = lib()
+    ws = torch.empty(max(int(L.nphm_mc_workspace_bytes(byref(p))), 256), device=dev, dtype=torch.uint8)
+    nv, nt = c_longlong(0), c_longlong(0)
+    with torch.cuda.device(dev):
+        check(L.nphm_mc_count(vol.data_ptr(), byref(p), ws.data_ptr(), byref(nv), byref(nt), _stream_ptr(dev)),
+              'nphm_mc_count')
+    return nv.value, nt.value, p, ws
+
+
+def marching_cubes_emit(volume: torch.Tensor, p: McParams, ws: torch.Tensor, n_verts: int, n_tris: int,
+                        vert_id_base: int):
+    vol = volume.contiguous()
+    dev = vol.device
+    verts = torch.empty(n_verts, 3, device=dev, dtype=torch.float64)
+    tris = torch.empty(n_tris, 3, device=dev, dtype=torch.int64)
+    if n_verts or n_tris:
+        with torch.cuda.device(dev):
+            check(lib().nphm_mc_emit(vol.data_ptr(), byref(p), ws.data_ptr(), int(vert_id_base), verts.data_ptr(),
+                                     tris.data_ptr(), _stream_ptr(dev)), 'nphm_mc_emit')
+    return verts, tris
+
+
+def marching_cubes_host(volume: np.ndarray, iso: float = 0.0, negate: bool = False):
+    """== ``mcubes.marching_cubes`` on a host array through the host-buffer C entry point."""
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    nx, ny, nz = vol.shape
+    nv, nt = c_longlong(0), c_longlong(0)
+    L = lib()
+    check(L.nphm_marching_cubes_host(vol.ctypes.data, nx, ny, nz, float(iso), int(negate), None, None,
+                                     byref(nv), byref(nt)), 'nphm_marching_cubes_host')
+    verts = np.empty((nv.value, 3), np.float64)
+    tris = np.empty((nt.value, 3), np.int64)
+    if nv.value or nt.value:
+        check(L.nphm_marching_cubes_host(vol.ctypes.data, nx, ny, nz, float(iso), int(negate), verts.ctypes.data,
+                                         tris.ctypes.data, byref(nv), byref(nt)), 'nphm_marching_cubes_host')
+    return verts, tris.view(np.uint64)

@@ -1,0 +1,72 @@
+// Handle types behind the C ABI.
+#pragma once
+#include "common.cuh"
+#include "simt.cuh"
+#include <algorithm>
+
+namespace nphm {
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);          // grows (never shrinks); contents are NOT preserved on growth
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer();
+};
+
+struct StackDims {
+    int n_lin, skip, cond_dim, cvec_stride, max_rows;
+    int in_total[kMaxLayers], N[kMaxLayers], Npad[kMaxLayers], K[kMaxLayers], folded[kMaxLayers], coff[kMaxLayers];
+    float scale[kMaxLayers];
+};
+
+struct NetWeights {
+    DeviceBuffer W[kMaxLayers], b[kMaxLayers];   // copies in the reference layout (used for the per-query constants)
+    DeviceBuffer Wt[kMaxLayers];                 // SIMT layout [set][k][Npad]
+    int load(const StackDims &s, int n_sets, const float *const *w_dev, const float *const *b_dev, cudaStream_t stream);
+};
+
+int build_stack(StackDims &s, int cond_dim, int hidden, int n_layers, int out_dim);
+void fill_descriptors(const StackDims &s, const NetWeights &w, int n_members, int n_symm, int lat_dim, int lat_glob,
+                      int lat_loc, FoldedNet &net, PackSpec &spec);
+
+}  // namespace nphm
+
+struct nphm_ensemble {
+    nphm_ensemble_config cfg;
+    int n_members = 0, n_sets = 0, lat_dim = 0;
+    bool loaded = false;
+    nphm::StackDims dims;
+    nphm::NetWeights weights;
+    nphm::FoldedNet net;
+    nphm::PackSpec spec;
+    nphm::DeviceBuffer pos_w[3], pos_b[3], mean_anchors;
+    // per-call scratch
+    nphm::DeviceBuffer anchors, cvec, axes, host_latent, host_volume;
+    // tensor-core path (tc_ensemble.cu)
+    nphm::DeviceBuffer tc_weights, tc_consts;
+    bool tc_ready = false;
+    // fitting (fit.cu)
+    nphm::DeviceBuffer fit_scratch;
+};
+
+struct nphm_mlp {
+    nphm_mlp_config cfg;
+    bool loaded = false;
+    nphm::StackDims dims;
+    nphm::NetWeights weights;
+    nphm::FoldedNet net;
+    nphm::PackSpec spec;
+    nphm::DeviceBuffer cvec;
+};
+
+namespace nphm {
+int ensemble_prepare(nphm_ensemble *h, const float *latents_dev, int n_queries, cudaStream_t stream);
+// tensor-core ensemble kernel (tc_ensemble.cu)
+bool tc_ensemble_supported(const nphm_ensemble *h);
+int tc_ensemble_pack(nphm_ensemble *h, cudaStream_t stream);
+int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream);
+}  // namespace nphm

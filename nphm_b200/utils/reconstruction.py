@@ -1,0 +1,48 @@
+"""Drop-in mirror of the reference module ``NPHM.utils.reconstruction``.
+
+  * ``create_grid_points_from_bounds``  src/NPHM/utils/reconstruction.py:5-20
+  * ``mesh_from_logits``                src/NPHM/utils/reconstruction.py:22-37  (mcubes.marching_cubes -> the
+    sm_100a marching-cubes kernels of ``nphm_b200/csrc/marching_cubes.cu``)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _native
+from .mesh import make_mesh
+
+
+def create_grid_points_from_bounds(minimun, maximum, res, scale=None):
+    """(res^3, 3) float64 grid, x slowest / z fastest, end points included."""
+    if scale is not None:
+        res = int(scale * res)
+        minimun = scale * minimun
+        maximum = scale * maximum
+    axes = [np.linspace(minimun[a], maximum[a], res) for a in range(3)]
+    pts = np.empty((res, res, res, 3), dtype=np.float64)
+    pts[..., 0] = axes[0][:, None, None]
+    pts[..., 1] = axes[1][None, :, None]
+    pts[..., 2] = axes[2][None, None, :]
+    return pts.reshape(-1, 3)
+
+
+def marching_cubes(volume, isovalue=0.0):
+    """== ``mcubes.marching_cubes(volume, isovalue)`` on the GPU: (verts (V,3) float64 in index units,
+    tris (T,3) uint64).  Accepts a numpy array (host round trip) or a CUDA tensor."""
+    if isinstance(volume, torch.Tensor) and volume.is_cuda:
+        v, t = _native.marching_cubes_device(volume.float(), isovalue)
+        return v.cpu().numpy(), t.cpu().numpy().view(np.uint64)
+    return _native.marching_cubes_host(np.asarray(volume), isovalue)
+
+
+def mesh_from_logits(logits, mini, maxi, resolution):
+    """SDF volume -> mesh.  Like the reference, NEGATES ``logits`` in place (caller's array), extracts the 0
+    level set of ``-sdf``, and maps index units to world units with ``step = (maxi-mini)/(resolution-1)``."""
+    logits = np.reshape(logits, (resolution,) * 3)
+    logits *= -1
+    vertices, triangles = marching_cubes(logits, 0.0)
+    step = (np.array(maxi) - np.array(mini)) / (resolution - 1)
+    vertices = vertices * np.expand_dims(step, axis=0)
+    vertices += [mini[0], mini[1], mini[2]]
+    return make_mesh(vertices, triangles)

@@ -1,0 +1,160 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA kernels, called through the C ABI
+(nphm_b200._native -> libnphm_b200.so), against the oracle and the golden vectors of the reference.
+Tolerance 1e-5 abs fp32 (north_star) - the kernels are expected to be ~1e-7."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import (MAXI, MINI, load_golden, make_deformation, make_ensemble, make_npm, sample_latent, sd_numpy)
+from oracle import nphm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _impls():
+    from nphm_b200 import _native
+    return ['simt', 'tc']
+
+
+def _engine_or_skip(dec, impl):
+    from nphm_b200 import _native
+    eng = dec.engine()
+    return eng
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('tag,seed,scale', [('a', 0, 1.0), ('b', 5, 2.0)])
+def test_ensemble_query_matches_reference_golden(cuda_device, impl, tag, seed, scale):
+    g = load_golden('ensemble.npz')
+    dec = make_ensemble(seed, scale, device=cuda_device)
+    x = torch.from_numpy(g['points_' + tag]).to(cuda_device).unsqueeze(0)
+    lat = torch.from_numpy(g['latent_' + tag]).to(cuda_device).reshape(1, -1)
+    eng = dec.engine()
+    s_eval, anc = eng.query(x, lat, eval_quirk=True, impl=impl)
+    s_train, _ = eng.query(x, lat, eval_quirk=False, impl=impl)
+    assert np.abs(anc.cpu().numpy()[0] - g['anchors_' + tag]).max() < 1e-6
+    e1 = np.abs(s_eval.cpu().numpy().reshape(-1) - g['sdf_eval_' + tag]).max()
+    e2 = np.abs(s_train.cpu().numpy().reshape(-1) - g['sdf_train_' + tag]).max()
+    print('ensemble %s %s max abs err eval %.3g train %.3g' % (impl, tag, e1, e2))
+    assert e1 < TOL and e2 < TOL
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_ensemble_matches_oracle_on_seeded_inputs(cuda_device, impl):
+    """Ragged sizes (not a multiple of the tile), batch of 3 queries with different latents, zero latent."""
+    dec = make_ensemble(3, 1.5, device=cuda_device)
+    p = O.EnsembleParams(sd_numpy(dec), load_golden('assets.npz')['anchors_39'])
+    rng = np.random.RandomState(11)
+    for n in (1, 37, 129, 1000):
+        pts = (rng.rand(3, n, 3) * (np.array(MAXI) - np.array(MINI)) + np.array(MINI)).astype(np.float32)
+        lats = np.stack([sample_latent(21).numpy() * 5, np.zeros(1344, np.float32), sample_latent(22).numpy() * 10])
+        sdf, anc = dec.engine().query(torch.from_numpy(pts).to(cuda_device), torch.from_numpy(lats).to(cuda_device),
+                                      eval_quirk=True, impl=impl)
+        for b in range(3):
+            ref, ref_anc = O.ensemble_forward(p, pts[b], lats[b], eval_mode=True)
+            assert np.abs(anc[b].cpu().numpy() - ref_anc).max() < 1e-6
+            err = np.abs(sdf[b].cpu().numpy().reshape(-1) - ref).max()
+            assert err < TOL, (n, b, err)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_module_forward_and_get_logits_dropin(cuda_device, impl, monkeypatch):
+    from nphm_b200.models.reconstruction import get_logits
+    from nphm_b200.utils.reconstruction import create_grid_points_from_bounds
+    monkeypatch.setenv('NPHM_B200_IMPL', impl)
+    g = load_golden('ensemble.npz')
+    dec = make_ensemble(0, device=cuda_device).eval()
+    grid = torch.from_numpy(create_grid_points_from_bounds(MINI, MAXI, 20)).to(cuda_device, dtype=torch.float)
+    grid = grid.reshape(1, -1, 3)
+    lat = torch.from_numpy(g['latent_a']).to(cuda_device)
+    logits, anchors = get_logits(dec, lat, grid, nbatch_points=3000, return_anchors=True)
+    assert logits.shape == (8000,) and logits.dtype == np.float32 and anchors.shape == (1, 39, 3)
+    assert np.abs(logits - g['logits20_a']).max() < TOL
+    # plain module call under no_grad: B x N x lat (materialised repeat, like the reference's get_logits does)
+    with torch.no_grad():
+        s, a = dec(grid[:, :777], lat.reshape(1, 1, -1).repeat(1, 777, 1), None)
+    assert s.shape == (1, 777, 1)
+    ref, _ = O.ensemble_forward(O.EnsembleParams(sd_numpy(dec), load_golden('assets.npz')['anchors_39']),
+                                grid[0, :777].cpu().numpy(), g['latent_a'], eval_mode=True)
+    assert np.abs(s.cpu().numpy().reshape(-1) - ref).max() < TOL
+    # weights updated in place -> engine repacks
+    with torch.no_grad():
+        dec.ensembled_deep_sdf.lin4.bias.add_(0.25)
+        s2, _ = dec(grid[:, :777], lat.reshape(1, 1, -1), None)
+    d = (s2 - s).cpu().numpy().reshape(-1)[:-1]
+    assert np.abs(d - 0.25).max() < 1e-3      # blend weights sum to ~1 near the head, background far away
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_grid_query_equals_explicit_points_and_shards(cuda_device, impl):
+    """In-kernel grid generation == float32(np.linspace) points; shards of the flat index range agree with the
+    whole (quirk positions follow the GLOBAL index)."""
+    from nphm_b200.utils.reconstruction import create_grid_points_from_bounds
+    dec = make_ensemble(0, device=cuda_device).eval()
+    lat = sample_latent(1).to(cuda_device)
+    res = 24
+    total = res ** 3
+    eng = dec.engine()
+    whole, _ = eng.query_grid(lat, MINI, MAXI, res, 0, total, quirk_period=2500, impl=impl)
+    pts = torch.from_numpy(create_grid_points_from_bounds(MINI, MAXI, res)).to(cuda_device, dtype=torch.float)
+    explicit, _ = eng.query(pts.reshape(1, -1, 3), lat.reshape(1, -1), eval_quirk=True, quirk_period=2500, impl=impl)
+    assert torch.equal(whole, explicit.reshape(-1))
+    parts = []
+    bounds = [0, 5000, 5001, 9999, total]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        part, _ = eng.query_grid(lat, MINI, MAXI, res, lo, hi - lo, quirk_period=2500, impl=impl)
+        parts.append(part)
+    assert torch.equal(torch.cat(parts), whole)
+
+
+def test_tc_and_simt_kernels_agree(cuda_device):
+    dec = make_ensemble(0, device=cuda_device).eval()
+    lat = sample_latent(1).to(cuda_device)
+    eng = dec.engine()
+    a, _ = eng.query_grid(lat, MINI, MAXI, 40, 0, 40 ** 3, quirk_period=25000, impl='simt')
+    b, _ = eng.query_grid(lat, MINI, MAXI, 40, 0, 40 ** 3, quirk_period=25000, impl='tc')
+    err = (a - b).abs().max().item()
+    print('tc vs simt max abs diff %.3g' % err)
+    assert err < 2e-6
+
+
+def test_deformation_and_npm_match_reference_golden(cuda_device):
+    d = load_golden('deform.npz')
+    dfn = make_deformation(cuda_device)
+    pts = torch.from_numpy(d['points']).to(cuda_device).unsqueeze(0)
+    cond = torch.cat([torch.from_numpy(d['latent_id']), torch.from_numpy(d['z_ex'])]).reshape(1, 1, -1).to(cuda_device)
+    anc = torch.from_numpy(d['anchors']).to(cuda_device).unsqueeze(0)
+    with torch.no_grad():
+        off, last = dfn(pts, cond, anc)
+        off_rep, _ = dfn(pts, cond.repeat(1, pts.shape[1], 1), anc.unsqueeze(1).repeat(1, pts.shape[1], 1, 1))
+    assert off.shape == (1, pts.shape[1], 3) and last.shape == (1, pts.shape[1], 1)
+    err = np.abs(off.cpu().numpy()[0] - d['offsets']).max()
+    print('deformation max abs err %.3g' % err)
+    assert err < TOL and torch.equal(off, off_rep)
+    assert np.abs(last.cpu().numpy().reshape(-1) - d['last']).max() < TOL
+    npm = make_npm(cuda_device)
+    with torch.no_grad():
+        out, none = npm(pts, torch.from_numpy(d['z_npm']).to(cuda_device).reshape(1, 1, -1))
+    assert none is None and np.abs(out.cpu().numpy().reshape(-1) - d['npm_out']).max() < TOL
+    # oracle on a ragged batch of 2 queries
+    rng = np.random.RandomState(5)
+    x = (rng.rand(2, 333, 3) - 0.5).astype(np.float32)
+    c = (rng.randn(2, 64) * 0.1).astype(np.float32)
+    got = npm.engine().query(torch.from_numpy(x).to(cuda_device), torch.from_numpy(c).to(cuda_device)).cpu().numpy()
+    mp = O.MlpParams(sd_numpy(npm))
+    for b in range(2):
+        assert np.abs(got[b] - O.mlp_forward(mp, x[b], c[b])).max() < TOL
+
+
+def test_deform_mesh_dropin(cuda_device):
+    from nphm_b200.models.reconstruction import deform_mesh
+    from nphm_b200.utils.mesh import SimpleMesh
+    d = load_golden('deform.npz')
+    dfn = make_deformation(cuda_device)
+    mesh = SimpleMesh(d['points'].astype(np.float64), np.array([[0, 1, 2], [2, 3, 4]]))
+    out = deform_mesh(mesh, dfn, torch.from_numpy(d['z_ex']).to(cuda_device).reshape(1, 1, -1),
+                      torch.from_numpy(d['anchors']).to(cuda_device).unsqueeze(0),
+                      lat_rep_shape=torch.from_numpy(d['latent_id']).to(cuda_device).reshape(1, 1, -1))
+    assert np.abs(np.asarray(out.vertices) - (d['points'] + d['offsets'])).max() < 2e-5
+    assert np.array_equal(np.asarray(out.faces), mesh.faces)

@@ -1,0 +1,144 @@
+"""CPU suite, part 2: host-side logic of the drop-in modules (composite path), API surface, and that the C-ABI
+library loads and exports every symbol include/nphm_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, make_deformation, make_ensemble, make_npm, mean_anchors
+
+
+def sd_hash(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].detach().cpu().numpy()).tobytes())
+    return h.hexdigest()
+
+
+def test_initialisation_is_bit_identical_to_reference():
+    g, d = load_golden('ensemble.npz'), load_golden('deform.npz')
+    assert sd_hash(make_ensemble(0).state_dict()) == str(g['sha256_a'])
+    assert sd_hash(make_ensemble(5, 2.0).state_dict()) == str(g['sha256_b'])
+    assert sd_hash(make_deformation().state_dict()) == str(d['sha256_def'])
+    assert sd_hash(make_npm().state_dict()) == str(d['sha256_npm'])
+
+
+def test_state_dict_contract():
+    sd = make_ensemble(0).state_dict()
+    assert sd['ensembled_deep_sdf.lin0.weight'].shape == (24, 200, 99)
+    assert sd['ensembled_deep_sdf.lin1.weight'].shape == (24, 101, 200)
+    assert sd['ensembled_deep_sdf.lin2.weight'].shape == (24, 200, 200)
+    assert sd['ensembled_deep_sdf.lin4.bias'].shape == (24, 1)
+    assert sd['mlp_pos.4.weight'].shape == (117, 256)
+    assert not any(k.startswith('anchors') or '_set_of_member' in k for k in sd)
+    dsd = make_deformation().state_dict()
+    assert dsd['compressor.0.weight'].shape == (32, 1461)
+    assert dsd['defDeepSDF.lin0.weight'].shape == (512, 235)
+    assert dsd['defDeepSDF.lin2.weight'].shape == (277, 512)
+    assert dsd['defDeepSDF.lin6.weight'].shape == (3, 512)
+    dec = make_ensemble(0)
+    assert (dec.lat_dim, dec.lat_dim_glob, dec.lat_dim_loc, dec.num_kps, dec.num_symm_pairs) == (1344, 64, 32, 39, 16)
+
+
+def test_composite_forward_matches_reference_outputs():
+    g = load_golden('ensemble.npz')
+    for tag, seed, scale in (('a', 0, 1.0), ('b', 5, 2.0)):
+        dec = make_ensemble(seed, scale)
+        x = torch.from_numpy(g['points_' + tag]).unsqueeze(0)
+        lat = torch.from_numpy(g['latent_' + tag]).reshape(1, 1, -1)
+        with torch.no_grad():
+            dec.eval()
+            s_eval, anc = dec(x, lat, None)
+            dec.train()
+            s_train, _ = dec(x, lat.repeat(1, x.shape[1], 1), None)     # materialised per-point latent
+        assert s_eval.shape == (1, x.shape[1], 1) and anc.shape == (1, 39, 3)
+        assert np.abs(s_eval.numpy().reshape(-1) - g['sdf_eval_' + tag]).max() < 1e-5
+        assert np.abs(s_train.numpy().reshape(-1) - g['sdf_train_' + tag]).max() < 1e-5
+        assert np.abs(anc.numpy()[0] - g['anchors_' + tag]).max() < 1e-6
+
+
+def test_composite_deformation_and_get_logits():
+    from nphm_b200.models.reconstruction import get_logits
+    from nphm_b200.utils.reconstruction import create_grid_points_from_bounds
+    d = load_golden('deform.npz')
+    dfn = make_deformation()
+    pts = torch.from_numpy(d['points']).unsqueeze(0)
+    cond = torch.cat([torch.from_numpy(d['latent_id']), torch.from_numpy(d['z_ex'])]).reshape(1, 1, -1)
+    with torch.no_grad():
+        off, last = dfn(pts, cond.repeat(1, pts.shape[1], 1), torch.from_numpy(d['anchors']).unsqueeze(0))
+        npm_out, none = make_npm()(pts, torch.from_numpy(d['z_npm']).reshape(1, 1, -1).repeat(1, pts.shape[1], 1))
+    assert none is None
+    assert np.abs(off.numpy()[0] - d['offsets']).max() < 1e-5 and np.abs(last.numpy().reshape(-1) - d['last']).max() < 1e-5
+    assert np.abs(npm_out.numpy().reshape(-1) - d['npm_out']).max() < 1e-5
+    g = load_golden('ensemble.npz')
+    dec = make_ensemble(0).eval()
+    grid = torch.from_numpy(create_grid_points_from_bounds([-.55, -.5, -.95], [0.55, 0.75, 0.4], 20)).float().unsqueeze(0)
+    logits = get_logits(dec, torch.from_numpy(g['latent_a']), grid, nbatch_points=3000)
+    assert logits.shape == (8000,) and logits.dtype == np.float32
+    assert np.abs(logits - g['logits20_a']).max() < 1e-5
+
+
+def test_autograd_flows_through_composite_path():
+    dec = make_ensemble(0).train()
+    x = torch.randn(1, 16, 3) * 0.2
+    x.requires_grad_(True)
+    z = torch.zeros(1, 1, 1344, requires_grad=True)
+    s, anc = dec(x, z, None)
+    (gx,) = torch.autograd.grad(s.sum(), x, create_graph=True)
+    (gx.pow(2).sum() + anc.sum()).backward()                      # double backward (eikonal-style)
+    assert z.grad is not None and torch.isfinite(z.grad).all() and z.grad.abs().sum() > 0
+
+
+def test_install_as_nphm_aliases():
+    import nphm_b200
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == 'NPHM' or k.startswith('NPHM.')}
+    try:
+        nphm_b200.install_as_nphm(force=True)
+        from NPHM.models.EnsembledDeepSDF import FastEnsembleDeepSDFMirrored as A
+        from NPHM.models.deepSDF import DeepSDF, DeformationNetwork      # noqa: F401
+        from NPHM.models.reconstruction import deform_mesh, get_logits, get_logits_backward      # noqa: F401
+        from NPHM.utils.reconstruction import create_grid_points_from_bounds, mesh_from_logits    # noqa: F401
+        from nphm_b200.models.EnsembledDeepSDF import FastEnsembleDeepSDFMirrored as B
+        assert A is B
+    finally:
+        for k in [k for k in sys.modules if k == 'NPHM' or k.startswith('NPHM.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_library_exports_every_declared_symbol():
+    from nphm_b200 import _native
+    header = open(os.path.join(ROOT, 'include', 'nphm_b200.h')).read()
+    declared = set(re.findall(r'\b(nphm_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    so = os.path.join(ROOT, 'nphm_b200', 'libnphm_b200.so')
+    if not os.path.exists(so):
+        pytest.fail('libnphm_b200.so not built: run __graft_entry__.build()')
+    lib = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.nphm_abi_version.restype = ctypes.c_int
+    assert lib.nphm_abi_version() == 1
+
+
+def test_fused_path_refuses_to_run_without_library(monkeypatch):
+    """The product path must fail loudly when the CUDA extension is missing."""
+    from nphm_b200 import _native
+    monkeypatch.setattr(_native, '_lib', None)
+    monkeypatch.setattr(_native, '_LIB_PATH', '/nonexistent/libnphm_b200.so')
+    with pytest.raises(_native.NativeError):
+        _native.lib()
+
+
+def test_mc_tables_identical_in_oracle_and_product():
+    a = open(os.path.join(ROOT, 'oracle', 'mc_tables_oracle.h')).read().split('\n', 4)[4]
+    b = open(os.path.join(ROOT, 'nphm_b200', 'csrc', 'mc_tables.h')).read().split('\n', 4)[4]
+    assert a == b
+    import subprocess, sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'gen_mc_tables.py')]).returncode == 0

@@ -1,0 +1,122 @@
+"""CPU suite, part 1: pin the ORACLE (oracle/) against the golden vectors produced by the reference itself
+(tests/golden/make_golden.py) and check the marching-cubes restatement through domain properties."""
+import numpy as np
+import torch
+
+from conftest import (load_golden, make_deformation, make_ensemble, make_npm, mesh_edge_stats, noise_volume,
+                      sd_numpy, sphere_volume)
+from oracle import nphm_oracle as O
+
+TOL = 1e-5          # north_star tolerance for SDF / deformation outputs (abs, fp32)
+
+
+def _params(seed, scale):
+    dec = make_ensemble(seed, scale)
+    a = load_golden('assets.npz')['anchors_39']
+    return O.EnsembleParams(sd_numpy(dec), a)
+
+
+def test_oracle_ensemble_matches_reference_outputs():
+    g = load_golden('ensemble.npz')
+    for tag, seed, scale in (('a', 0, 1.0), ('b', 5, 2.0)):
+        p = _params(seed, scale)
+        pts, lat = g['points_' + tag], g['latent_' + tag]
+        s_eval, anc = O.ensemble_forward(p, pts, lat, eval_mode=True)
+        s_train, _ = O.ensemble_forward(p, pts, lat, eval_mode=False)
+        assert np.abs(anc - g['anchors_' + tag]).max() < 1e-6
+        assert np.abs(s_eval - g['sdf_eval_' + tag]).max() < TOL
+        assert np.abs(s_train - g['sdf_train_' + tag]).max() < TOL
+        # the eval quirk only touches the last point of the call
+        assert np.array_equal(s_eval[:-1], s_train[:-1]) and s_eval[-1] != s_train[-1]
+
+
+def test_oracle_get_logits_chunk_quirk():
+    g = load_golden('ensemble.npz')
+    p = _params(0, 1.0)
+    grid = O.linspace_grid([-.55, -.5, -.95], [0.55, 0.75, 0.4], 20)
+    out = O.get_logits(p, g['latent_a'], grid, nbatch_points=3000)
+    assert np.abs(out - g['logits20_a']).max() < TOL
+    train = O.get_logits(p, g['latent_a'], grid, nbatch_points=3000, eval_mode=False)
+    differs = np.nonzero(out != train)[0]
+    assert set(differs.tolist()) <= {2999, 5999, 7999} and 7999 in differs
+
+
+def test_oracle_grid_matches_reference():
+    g = load_golden('ensemble.npz')
+    assert np.array_equal(O.linspace_grid([-.55, -.5, -.95], [0.55, 0.75, 0.4], 5), g['grid5'])
+
+
+def test_oracle_deformation_and_npm():
+    g = load_golden('deform.npz')
+    dfn = make_deformation()
+    off = O.deformation_forward(sd_numpy(dfn), g['points'], g['latent_id'], g['z_ex'], g['anchors'])
+    assert np.abs(off - g['offsets']).max() < TOL
+    npm = make_npm()
+    out = O.mlp_forward(O.MlpParams(sd_numpy(npm)), g['points'], g['z_npm'])
+    assert np.abs(out[:, 0] - g['npm_out']).max() < TOL
+
+
+def test_oracle_adam_matches_torch():
+    rng = np.random.RandomState(0)
+    p0 = rng.randn(300).astype(np.float32) * 0.1
+    t = torch.tensor(p0.copy(), requires_grad=True)
+    opt = torch.optim.Adam([t], lr=0.01)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    lr = 0.01
+    for step in range(1, 8):
+        grad = (rng.randn(300) * (10.0 ** rng.randint(-6, 1))).astype(np.float32)
+        if step == 4:
+            lr /= 2
+            for gr in opt.param_groups:
+                gr['lr'] /= 2
+        t.grad = torch.tensor(grad)
+        opt.step()
+        p, m, v = O.adam_step(p, grad, m, v, step, lr)
+        assert np.abs(p - t.detach().numpy()).max() < 2e-7
+
+
+def test_mc_oracle_sphere_is_closed_manifold():
+    vol = sphere_volume(24)
+    verts, tris = O.marching_cubes(vol, 0.0)
+    assert len(verts) > 0 and tris.max() == len(verts) - 1
+    dup, unmatched = mesh_edge_stats(tris)
+    assert dup == 0 and unmatched == 0
+    assert len(verts) - 3 * len(tris) // 2 + len(tris) == 2          # Euler characteristic of a sphere
+    # vertices lie on grid edges (two integer coordinates) and close to the sphere
+    frac = np.abs(verts - np.round(verts))
+    assert (np.sort(frac, axis=1)[:, :2] < 1e-12).all()
+    world = verts / 23.0 - 0.5
+    r = np.linalg.norm(world - np.array([0.03, -0.02, 0.01]), axis=1)
+    assert np.abs(r - 0.4).max() < 2e-3
+    # every referenced vertex is used, numbering is in creation order (first use is increasing)
+    first_use = np.full(len(verts), -1)
+    flat = tris.reshape(-1).astype(np.int64)
+    first_use[flat[::-1]] = np.arange(len(flat))[::-1]
+    assert (first_use >= 0).all()
+
+
+def test_mc_oracle_negate_and_all_cases():
+    vol = noise_volume((9, 7, 8))
+    v1, t1 = O.marching_cubes(vol, 0.1)
+    v2, t2 = O.marching_cubes(-vol, -0.1, negate=True)      # -(-vol) <= -0.1  <=>  vol <= -0.1 ... different set
+    assert len(t1) > 0 and len(t2) > 0
+    va, ta = O.marching_cubes(-vol, 0.0)
+    vb, tb = O.marching_cubes(vol, 0.0, negate=True)
+    assert np.array_equal(va, vb) and np.array_equal(ta, tb)
+    # interior half edges pair up; unmatched ones must lie on the volume boundary
+    dup, _ = mesh_edge_stats(ta)
+    assert dup == 0
+    # degenerate sizes
+    for shape in ((1, 5, 5), (5, 1, 5), (2, 2, 2)):
+        v, t = O.marching_cubes(noise_volume(shape), 0.0)
+        if 1 in shape:
+            assert len(v) == 0 and len(t) == 0
+
+
+def test_mc_oracle_mesh_from_logits_negates_in_place():
+    vol = sphere_volume(12)
+    flat = vol.reshape(-1).copy()
+    keep = flat.copy()
+    verts, tris = O.mesh_from_logits(flat, [-.55, -.5, -.95], [0.55, 0.75, 0.4], 12)
+    assert np.array_equal(flat, -keep)
+    assert verts[:, 0].min() >= -.55 and verts[:, 2].max() <= 0.4 and len(tris) > 0
