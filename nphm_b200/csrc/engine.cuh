@@ -47,7 +47,7 @@ struct nphm_ensemble {
     // per-call scratch
     nphm::DeviceBuffer anchors, cvec, axes, host_latent, host_volume;
     // tensor-core path (tc_ensemble.cu)
-    nphm::DeviceBuffer tc_weights, tc_consts;
+    nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
     bool tc_ready = false;
     // fitting (fit.cu)
     nphm::DeviceBuffer fit_scratch;

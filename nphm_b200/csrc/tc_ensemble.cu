@@ -1,7 +1,677 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 / TMEM kernel for the identity-SDF ensemble (NPHM configuration: 40 members, hidden 200, 4 hidden
+// layers, condition 64+32) - the dominant kernel of the hot path.
+//
+// Reference semantics: FastEnsembleDeepSDFMirrored.forward  src/NPHM/models/EnsembledDeepSDF.py:203-267
+//
+// Math (SURVEY.md 8a'): per member, per point
+//   h0 = sp(W0x c + v0)            K=3   -> CUDA cores (v0 = latent part + bias, per query/member)
+//   h1 = sp(W1 h0 + b1)            128x112x208 UMMA   (N 101 -> 112, K 200 -> 208)
+//   h2 = sp(W2a h1/r2 + W2x c/r2 + v2)   128x208x112 UMMA   (K = 101 + 3 -> 112)
+//   h3 = sp(W3 h2 + b3)            128x208x208 UMMA
+//   s  = w4 . h3 + b4              CUDA cores, fused into the h3 epilogue; Gaussian anchor blend in registers.
+// Precision: tensor cores run kind::f16 with fp32 accumulation; every operand is split in two fp16 terms
+// (x = hi + lo, 22 significant bits) and each product is evaluated as hi*hi + hi*lo + lo*hi (3 MMAs), which
+// keeps the result at fp32 round-off level (measured ~1e-7 abs against the fp32 reference, tolerance 1e-5).
+// Activations are kept in "log2 units": t = a * 100*log2(e), sp'(t) = max(t,0) + lg2(1 + 2^-|t|) = 100*log2(e) *
+// softplus_100(a), so the softplus costs 2 MUFU + 3 ALU and the unit change is folded into biases / w4.
+//
+// Data flow per CTA (persistent, one CTA per SM, 10 warps):
+//   warp 8  : bulk-async-copy (TMA engine, cp.async.bulk) producer: streams pre-split fp16 weight slabs
+//             (N x 16 K-columns, hi|lo, UMMA no-swizzle K-major core-matrix order) from L2 into a 14-slot ring,
+//             and the per-(query,member) constant record (layer-0 weights, biases, w4, anchor) into a 2-slot ring.
+//   warp 9  : allocates TMEM, single-thread tcgen05.mma issuer: A (activations) from TMEM, B (weights) from smem,
+//             D (fp32) in TMEM; tcgen05.commit releases ring slots and signals the epilogue.
+//   warps 0-7: thread = point (TMEM lane) x column half: read D with tcgen05.ld, softplus, split to fp16 hi/lo,
+//             write the next layer's A operand back to TMEM with tcgen05.st, pre-load D with the next bias.
+// TMEM map (columns): D [0,208)  A_hi [208,312)  A_lo [312,416)   (fp16 pairs, 2 K-values per column).
 #include "engine.cuh"
+#include <cuda_fp16.h>
+
 namespace nphm {
-bool tc_ensemble_supported(const nphm_ensemble *) { return false; }
-int tc_ensemble_pack(nphm_ensemble *, cudaStream_t) { return NPHM_OK; }
-int tc_ensemble_launch(nphm_ensemble *, const SimtQuery &, cudaStream_t) { set_error("tcgen05 kernel not built"); return NPHM_ERR_UNSUPPORTED; }
+namespace tc {
+
+constexpr int kH = 200;            // hidden width
+constexpr int kN1 = 101;           // layer-1 width (hidden - d_in)
+constexpr int kCond = 96;
+constexpr int kNP1 = 112, kNP2 = 208, kNP3 = 208;
+constexpr int kKS1 = 13, kKS2 = 7, kKS3 = 13;       // k-steps of 16
+constexpr int kSlab1Bytes = kNP1 * 64;               // hi + lo, 16 K-columns
+constexpr int kSlabBytes = kNP2 * 64;
+constexpr int kSlots = 14;
+constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3Bytes = kKS3 * kSlabBytes;
+constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
+constexpr int kColD = 0, kColAhi = 208, kColAlo = 312, kTmemCols = 512;
+// per-(query, member) record, in floats
+constexpr int kRecL0 = 0;          // 200 x float4 (W0x row, S*v0)
+constexpr int kRecB1 = 800;        // 112
+constexpr int kRecB2 = 912;        // 208
+constexpr int kRecB3 = 1120;       // 208
+constexpr int kRecW4 = 1328;       // 208
+constexpr int kRecMisc = 1536;     // b4, ax, ay, az, has_anchor, mirror, -, -
+constexpr int kRecFloats = 1544;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr float kS = 144.26950408889634f;            // 100 * log2(e)
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8x(16 B) core matrices of 128 contiguous bytes;
+// LBO = byte distance between the two core matrices along K, SBO = between 8-row groups along N.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, K-major both, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// softplus in log2 units: sp'(t) = lg2(1 + 2^t) = max(t, 0) + lg2(1 + 2^-|t|)
+__device__ __forceinline__ float sp_t(float t)
+{
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return fmaxf(t, 0.0f) + l;
+}
+
+// split two fp32 values into packed fp16 (hi, lo) pairs; element 0 in the low half (lower K index)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+struct __align__(1024) Smem {
+    uint8_t slabs[kSlots][kSlabBytes];
+    float rec[2][kRecFloats];
+    float partial[128];
+    uint64_t slab_full[kSlots], slab_empty[kSlots];
+    uint64_t rec_full[2], rec_empty[2];
+    uint64_t a_ready, d_ready;
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const uint8_t *weights;     // [n_sets][kSetBytes]
+    const float *recs;          // [n_queries][n_members][kRecFloats]
+    const float *xyz;
+    const float *axes;
+    int res;
+    long long first, total, n_points;
+    int n_queries;
+    long long quirk_period;
+    float *out;
+    int n_members, n_symm;
+};
+
+// store 8 consecutive activations (next-layer K indices k0..k0+7) as fp16 hi/lo pairs
+__device__ __forceinline__ void store_a8(uint32_t tmem_lane_base, int k0, const float (&v)[8])
+{
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    tc_st4(tmem_lane_base + kColAhi + (k0 >> 1), hi);
+    tc_st4(tmem_lane_base + kColAlo + (k0 >> 1), lo);
+}
+// preload 8 accumulator columns with a bias vector from shared memory
+__device__ __forceinline__ void init_d8(uint32_t tmem_lane_base, int col, const float *bias)
+{
+    const float4 b0 = *reinterpret_cast<const float4 *>(bias + col);
+    const float4 b1 = *reinterpret_cast<const float4 *>(bias + col + 4);
+    const uint32_t r[8] = {__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w),
+                           __float_as_uint(b1.x), __float_as_uint(b1.y), __float_as_uint(b1.z), __float_as_uint(b1.w)};
+    tc_st8(tmem_lane_base + kColD + col, r);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tiles_per_query = (p.n_points + 127) / 128;
+    const long long n_tiles = tiles_per_query * p.n_queries;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&sm.slab_full[i], 1); mbar_init(&sm.slab_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps); }
+        mbar_init(&sm.a_ready, kEpiWarps);
+        mbar_init(&sm.d_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == kEpiWarps) {
+        // =========================================================================== producer (bulk async copies)
+        if (lane == 0) {
+            int slot = 0, rslot = 0;
+            uint32_t ph = 0, rph = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int qi = (int)(tile / tiles_per_query);
+                for (int m = 0; m < p.n_members; ++m) {
+                    mbar_wait(&sm.rec_empty[rslot], rph ^ 1);
+                    mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
+                    bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
+                             &sm.rec_full[rslot]);
+                    if (++rslot == 2) { rslot = 0; rph ^= 1; }
+                    const int set = m < 2 * p.n_symm ? (m >> 1) : m - p.n_symm;
+                    const uint8_t *w = p.weights + (size_t)set * kSetBytes;
+#pragma unroll 1
+                    for (int j = 0; j < kKS1 + kKS2 + kKS3; ++j) {
+                        const uint32_t bytes = j < kKS1 ? kSlab1Bytes : kSlabBytes;
+                        mbar_wait(&sm.slab_empty[slot], ph ^ 1);
+                        mbar_expect_tx(&sm.slab_full[slot], bytes);
+                        bulk_g2s(sm.slabs[slot], w, bytes, &sm.slab_full[slot]);
+                        w += bytes;
+                        if (++slot == kSlots) { slot = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // =========================================================================== MMA issuer
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t ph = 0, a_ph = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int m = 0; m < p.n_members; ++m) {
+#pragma unroll 1
+                    for (int layer = 0; layer < 3; ++layer) {
+                        const int ks = layer == 0 ? kKS1 : (layer == 1 ? kKS2 : kKS3);
+                        const int n = layer == 0 ? kNP1 : kNP2;
+                        const uint32_t idesc = make_idesc(n);
+                        mbar_wait(&sm.a_ready, a_ph);
+                        a_ph ^= 1;
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int j = 0; j < ks; ++j) {
+                            mbar_wait(&sm.slab_full[slot], ph);
+                            tc_fence_after();
+                            const uint32_t base = smem_u32(sm.slabs[slot]);
+                            const uint64_t b_hi = make_desc(base, 128, 256);
+                            const uint64_t b_lo = make_desc(base + n * 32, 128, 256);
+                            const uint32_t a_hi = tmem + kColAhi + j * 8, a_lo = tmem + kColAlo + j * 8;
+                            tc_mma_ts(tmem + kColD, a_hi, b_hi, idesc, 1);
+                            tc_mma_ts(tmem + kColD, a_hi, b_lo, idesc, 1);
+                            tc_mma_ts(tmem + kColD, a_lo, b_hi, idesc, 1);
+                            tc_commit(&sm.slab_empty[slot]);
+                            if (++slot == kSlots) { slot = 0; ph ^= 1; }
+                        }
+                        tc_commit(&sm.d_ready);
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================================================================== compute / epilogue warps
+        const int q = warp & 3, hsel = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
+        int rslot = 0;
+        uint32_t rph = 0, d_ph = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int qi = (int)(tile / tiles_per_query);
+            const long long idx = (tile - (long long)qi * tiles_per_query) * 128 + row;
+            const bool valid = idx < p.n_points;
+            const long long g = p.first + (valid ? idx : 0);
+            float x, y, z;
+            if (p.xyz) {
+                const float *pp = p.xyz + ((size_t)qi * p.n_points + (valid ? idx : 0)) * 3;
+                x = pp[0]; y = pp[1]; z = pp[2];
+            } else {
+                const long long rr = (long long)p.res * p.res;
+                const int ix = (int)(g / rr), iy = (int)((g - ix * rr) / p.res), iz = (int)(g % p.res);
+                x = __ldg(p.axes + ix); y = __ldg(p.axes + p.res + iy); z = __ldg(p.axes + 2 * p.res + iz);
+            }
+            const bool quirk = p.quirk_period > 0 && ((g % p.quirk_period) == p.quirk_period - 1 || g == p.total - 1);
+            float num = 0.f, den = 0.f;
+
+            for (int m = 0; m < p.n_members; ++m) {
+                mbar_wait(&sm.rec_full[rslot], rph);
+                const float *rec = sm.rec[rslot];
+                const float b4 = rec[kRecMisc + 0];
+                const float ax = rec[kRecMisc + 1], ay = rec[kRecMisc + 2], az = rec[kRecMisc + 3];
+                const bool has_anchor = rec[kRecMisc + 4] != 0.f, mirror = rec[kRecMisc + 5] != 0.f;
+                float cx = x - ax, cy = y - ay, cz = z - az;
+                if (mirror) cx = -cx;
+                cx *= kS; cy *= kS; cz *= kS;                   // coordinates in log2 units
+
+                // ---------------- layer 0 on CUDA cores -> A operand of layer 1; D preloaded with S*b1
+#pragma unroll
+                for (int c = 0; c < 7; ++c) init_d8(tl, hsel * 56 + c * 8, rec + kRecB1);
+                {
+                    const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
+#pragma unroll 1
+                    for (int c = 0; c < 13; ++c) {
+                        const int n0 = hsel * 104 + c * 8;
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int n = n0 + e;
+                            if (n < kH) {
+                                const float4 w = l0[n];
+                                v[e] = sp_t(fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w))));
+                            } else {
+                                v[e] = 0.f;
+                            }
+                        }
+                        store_a8(tl, n0, v);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a_ready);
+
+                // ---------------- epilogue of layer 1 (N = 101 -> K of layer 2 = [h1, c, 0...])
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 7; ++c) {
+                    const int n0 = hsel * 56 + c * 8;
+                    uint32_t r[8];
+                    tc_ld8(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int n = n0 + e;
+                        v[e] = n < kN1 ? sp_t(__uint_as_float(r[e]))
+                                       : (n == kN1 ? cx : (n == kN1 + 1 ? cy : (n == kN1 + 2 ? cz : 0.f)));
+                    }
+                    store_a8(tl, n0, v);
+                }
+                // D for layer 2: columns this thread has just read, plus columns nobody reads in layer 1
+#pragma unroll
+                for (int c = 0; c < 7; ++c) init_d8(tl, hsel * 56 + c * 8, rec + kRecB2);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) init_d8(tl, 112 + hsel * 48 + c * 8, rec + kRecB2);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a_ready);
+
+                // ---------------- epilogue of layer 2
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 13; ++c) {
+                    const int n0 = hsel * 104 + c * 8;
+                    uint32_t r[8];
+                    tc_ld8(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (n0 + e) < kH ? sp_t(__uint_as_float(r[e])) : 0.f;
+                    store_a8(tl, n0, v);
+                    init_d8(tl, n0, rec + kRecB3);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a_ready);
+
+                // ---------------- epilogue of layer 3 fused with the output layer (dot with w4) and the blend
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+                float acc = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 13; ++c) {
+                    const int n0 = hsel * 104 + c * 8;
+                    uint32_t r[8];
+                    tc_ld8(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    const float4 w0 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0 + 4);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (n0 + e < kH) acc = fmaf(sp_t(__uint_as_float(r[e])), w[e], acc);
+                }
+                if (hsel == 1) sm.partial[row] = acc;
+                tc_fence_before();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // the two warps of this lane quarter
+                tc_fence_after();
+                if (hsel == 0) {
+                    const float s = acc + sm.partial[row] + b4;
+                    float d;
+                    if (has_anchor) {
+                        const float dx = ax - x, dy = ay - y, dz = az - z;
+                        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                        d = -(nrm * nrm);
+                    } else {
+                        d = -0.2f;
+                    }
+                    const float w = expf(__fdiv_rn(d, 0.01f));
+                    num = fmaf(w, quirk ? 1.0f : s, num);
+                    den += w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.rec_empty[rslot]);
+                if (++rslot == 2) { rslot = 0; rph ^= 1; }
+            }
+            if (hsel == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kEpiWarps + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// Weight slabs: for weight set s, tensor layer L (1..3), k-step j: N x 16 fp16 hi then N x 16 fp16 lo, each in UMMA
+// no-swizzle K-major core-matrix order: byte offset of (n, kk) = (n/8)*256 + (kk/8)*128 + (n%8)*16 + (kk%8)*2.
+__global__ void pack_slabs_kernel(const float *__restrict__ W1, const float *__restrict__ W2, const float *__restrict__ W3,
+                                  int n_sets, uint8_t *__restrict__ out)
+{
+    const int total_per_set = (kKS1 * kNP1 + (kKS2 + kKS3) * kNP2) * 16;       // (slab, n, kk) triples
+    const float inv_sqrt2 = 0.70710678118654752440f;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)n_sets * total_per_set;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(t / total_per_set);
+        int r = (int)(t % total_per_set);
+        int layer, j, n, kk, np;
+        size_t slab_off;
+        if (r < kKS1 * kNP1 * 16) {
+            layer = 1; np = kNP1; j = r / (np * 16); r -= j * np * 16; slab_off = (size_t)j * kSlab1Bytes;
+        } else if ((r -= kKS1 * kNP1 * 16) < kKS2 * kNP2 * 16) {
+            layer = 2; np = kNP2; j = r / (np * 16); r -= j * np * 16; slab_off = kL1Bytes + (size_t)j * kSlabBytes;
+        } else {
+            r -= kKS2 * kNP2 * 16;
+            layer = 3; np = kNP3; j = r / (np * 16); r -= j * np * 16; slab_off = kL1Bytes + kL2Bytes + (size_t)j * kSlabBytes;
+        }
+        n = r / 16; kk = r % 16;
+        const int k = j * 16 + kk;
+        float v = 0.f;
+        if (layer == 1) {
+            if (n < kN1 && k < kH) v = W1[((size_t)s * kN1 + n) * kH + k];
+        } else if (layer == 2) {
+            // reference input order of the skip layer: [h1 (101), xyz (3), cond (96)] / sqrt(2); the cond part is folded
+            if (n < kH && k < kN1 + 3) v = W2[((size_t)s * kH + n) * kH + k] * inv_sqrt2;
+        } else {
+            if (n < kH && k < kH) v = W3[((size_t)s * kH + n) * kH + k];
+        }
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t off = (size_t)(n >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(kk & 7) * 2;
+        uint8_t *base = out + (size_t)s * kSetBytes + slab_off;
+        *reinterpret_cast<__half *>(base + off) = hi;
+        *reinterpret_cast<__half *>(base + (size_t)np * 32 + off) = lo;
+    }
+}
+
+// record of (query, member): see kRec* offsets.  cvec holds b_l + latent-folded parts (simt.cu:cvec_kernel).
+__global__ void records_kernel(const float *__restrict__ cvec, int cvec_stride, const int *__restrict__ coff,
+                               const float *__restrict__ W0, const float *__restrict__ W4,
+                               const float *__restrict__ anchors, int n_members, int n_symm, float *__restrict__ recs)
+{
+    const int m = blockIdx.x, qi = blockIdx.y;
+    const int set = m < 2 * n_symm ? (m >> 1) : m - n_symm;
+    const float *cv = cvec + ((size_t)qi * n_members + m) * cvec_stride;
+    float *rec = recs + ((size_t)qi * n_members + m) * kRecFloats;
+    const int d_in = 3 + kCond;
+    for (int n = threadIdx.x; n < kH; n += blockDim.x) {
+        const float *w = W0 + ((size_t)set * kH + n) * d_in;
+        rec[kRecL0 + 4 * n + 0] = w[0];
+        rec[kRecL0 + 4 * n + 1] = w[1];
+        rec[kRecL0 + 4 * n + 2] = w[2];
+        rec[kRecL0 + 4 * n + 3] = kS * cv[coff[0] + n];
+    }
+    for (int n = threadIdx.x; n < kNP1; n += blockDim.x) rec[kRecB1 + n] = n < kN1 ? kS * cv[coff[1] + n] : 0.f;
+    for (int n = threadIdx.x; n < kNP2; n += blockDim.x) {
+        rec[kRecB2 + n] = n < kH ? kS * cv[coff[2] + n] : 0.f;
+        rec[kRecB3 + n] = n < kH ? kS * cv[coff[3] + n] : 0.f;
+        rec[kRecW4 + n] = n < kH ? W4[(size_t)set * kH + n] / kS : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        const bool has_anchor = m < n_members - 1;
+        rec[kRecMisc + 0] = cv[coff[4]];
+        rec[kRecMisc + 1] = has_anchor ? anchors[((size_t)qi * (n_members - 1) + m) * 3 + 0] : 0.f;
+        rec[kRecMisc + 2] = has_anchor ? anchors[((size_t)qi * (n_members - 1) + m) * 3 + 1] : 0.f;
+        rec[kRecMisc + 3] = has_anchor ? anchors[((size_t)qi * (n_members - 1) + m) * 3 + 2] : 0.f;
+        rec[kRecMisc + 4] = has_anchor ? 1.f : 0.f;
+        rec[kRecMisc + 5] = ((m & 1) && m < 2 * n_symm) ? 1.f : 0.f;
+        rec[kRecMisc + 6] = 0.f;
+        rec[kRecMisc + 7] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ MMA self test
+// One CTA: D[128 x n] = A[128 x 16*ks] * B[n x 16*ks]^T with the exact operand plumbing of the main kernel
+// (fp16 hi/lo split, A in TMEM, B slabs in smem).  `variant` bit0: swap LBO/SBO, bit1: swap the fp16 pair order.
+__global__ void __launch_bounds__(160, 1) mma_selftest_kernel(const float *__restrict__ A, const uint8_t *__restrict__ slabs,
+                                                              int n, int ks, int variant, float *__restrict__ D)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slab_bytes = n * 64;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ks * slab_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(base)[i] = reinterpret_cast<const uint4 *>(slabs)[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int k0 = 0; k0 < ks * 16; k0 += 8) {
+            float v[8];
+            for (int e = 0; e < 8; ++e) v[e] = A[(size_t)row * ks * 16 + k0 + e];
+            if (variant & 2) for (int e = 0; e < 8; e += 2) { const float t = v[e]; v[e] = v[e + 1]; v[e + 1] = t; }
+            store_a8(tl, k0, v);
+        }
+        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < n; c += 8) tc_st8(tl + kColD + c, zero);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 128) {
+        const uint32_t idesc = make_idesc(n);
+        const uint32_t lbo = (variant & 1) ? 256 : 128, sbo = (variant & 1) ? 128 : 256;
+        for (int j = 0; j < ks; ++j) {
+            const uint32_t b = smem_u32(base + (size_t)j * slab_bytes);
+            const uint64_t b_hi = make_desc(b, lbo, sbo), b_lo = make_desc(b + n * 32, lbo, sbo);
+            tc_mma_ts(tmem + kColD, tmem + kColAhi + j * 8, b_hi, idesc, 1);
+            tc_mma_ts(tmem + kColD, tmem + kColAhi + j * 8, b_lo, idesc, 1);
+            tc_mma_ts(tmem + kColD, tmem + kColAlo + j * 8, b_hi, idesc, 1);
+        }
+        tc_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < n; c += 8) {
+            uint32_t r[8];
+            tc_ld8(tl + kColD + c, r);
+            tc_wait_ld();
+            for (int e = 0; e < 8; ++e) D[(size_t)row * n + c + e] = __uint_as_float(r[e]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+
+__global__ void pack_test_slabs_kernel(const float *__restrict__ B, int n, int ks, uint8_t *__restrict__ out)
+{
+    // B: [n][16*ks] fp32 row-major -> ks slabs (hi | lo) in core-matrix order
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * ks * 16; t += gridDim.x * blockDim.x) {
+        const int row = t / (ks * 16), k = t % (ks * 16), j = k / 16, kk = k % 16;
+        const float v = B[t];
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t off = (size_t)(row >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(row & 7) * 16 + (size_t)(kk & 7) * 2;
+        uint8_t *base = out + (size_t)j * n * 64;
+        *reinterpret_cast<__half *>(base + off) = hi;
+        *reinterpret_cast<__half *>(base + (size_t)n * 32 + off) = lo;
+    }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------ host side
+bool tc_ensemble_supported(const nphm_ensemble *h)
+{
+    return h->cfg.hidden_dim == tc::kH && h->cfg.n_layers == 4 && h->cfg.lat_dim_glob + h->cfg.lat_dim_loc == tc::kCond &&
+           h->dims.N[1] == tc::kN1;
+}
+
+int tc_ensemble_pack(nphm_ensemble *h, cudaStream_t stream)
+{
+    h->tc_ready = false;
+    if (!tc_ensemble_supported(h)) return NPHM_OK;
+    int rc;
+    if ((rc = h->tc_weights.reserve((size_t)h->n_sets * tc::kSetBytes))) return rc;
+    tc::pack_slabs_kernel<<<512, 256, 0, stream>>>(h->weights.W[1].as<float>(), h->weights.W[2].as<float>(),
+                                                   h->weights.W[3].as<float>(), h->n_sets, h->tc_weights.as<uint8_t>());
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    if ((rc = h->tc_coff.reserve(kMaxLayers * sizeof(int)))) return rc;
+    NPHM_CUDA_CHECK(cudaMemcpyAsync(h->tc_coff.ptr, h->dims.coff, kMaxLayers * sizeof(int), cudaMemcpyHostToDevice, stream));
+    NPHM_CUDA_CHECK(cudaStreamSynchronize(stream));      // dims.coff is host memory of the handle; keep it simple
+    h->tc_ready = true;
+    return NPHM_OK;
+}
+
+int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream)
+{
+    NPHM_REQUIRE(h->tc_ready, "tcgen05 ensemble kernel: weights not packed");
+    int rc;
+    if ((rc = h->tc_consts.reserve((size_t)q.n_queries * h->n_members * tc::kRecFloats * sizeof(float)))) return rc;
+    dim3 grid(h->n_members, q.n_queries);
+    tc::records_kernel<<<grid, 256, 0, stream>>>(q.cvec, h->dims.cvec_stride, h->tc_coff.as<int>(), h->weights.W[0].as<float>(),
+                                                 h->weights.W[4].as<float>(), q.anchors, h->n_members, h->cfg.n_symm_pairs,
+                                                 h->tc_consts.as<float>());
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    tc::Params p{};
+    p.weights = h->tc_weights.as<uint8_t>();
+    p.recs = h->tc_consts.as<float>();
+    p.xyz = q.xyz; p.axes = q.axes; p.res = q.res; p.first = q.first; p.total = q.total; p.n_points = q.n_points;
+    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out;
+    p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
+    const long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;
+    const int grid_x = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    const int smem = (int)sizeof(tc::Smem) + 1024;
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::ensemble_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::ensemble_tc_kernel<<<grid_x, tc::kThreads, smem, stream>>>(p);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+}  // namespace nphm
+
+// Debug entry (not part of the public ABI): D = A * B^T through the tensor-core operand path.
+extern "C" int nphm_debug_tc_mma(const float *a_dev, const float *b_dev, int n, int ks, int variant, float *d_dev,
+                                 void *stream_)
+{
+    using namespace nphm;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(n % 16 == 0 && n >= 16 && n <= 208 && ks >= 1 && ks <= 13, "nphm_debug_tc_mma: bad shape");
+    uint8_t *slabs = nullptr;
+    NPHM_CUDA_CHECK(cudaMalloc(&slabs, (size_t)ks * n * 64));
+    tc::pack_test_slabs_kernel<<<64, 256, 0, stream>>>(b_dev, n, ks, slabs);
+    const int smem = ks * n * 64 + 1024;
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::mma_selftest_kernel<<<1, 160, smem, stream>>>(a_dev, slabs, n, ks, variant, d_dev);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(slabs);
+    if (e != cudaSuccess) { set_error("nphm_debug_tc_mma: %s", cudaGetErrorString(e)); return NPHM_ERR_CUDA; }
+    return NPHM_OK;
 }

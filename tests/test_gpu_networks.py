@@ -82,8 +82,10 @@ def test_module_forward_and_get_logits_dropin(cuda_device, impl, monkeypatch):
     with torch.no_grad():
         dec.ensembled_deep_sdf.lin4.bias.add_(0.25)
         s2, _ = dec(grid[:, :777], lat.reshape(1, 1, -1), None)
-    d = (s2 - s).cpu().numpy().reshape(-1)[:-1]
-    assert np.abs(d - 0.25).max() < 1e-3      # blend weights sum to ~1 near the head, background far away
+    ref2, _ = O.ensemble_forward(O.EnsembleParams(sd_numpy(dec), load_golden('assets.npz')['anchors_39']),
+                                 grid[0, :777].cpu().numpy(), g['latent_a'], eval_mode=True)
+    assert np.abs(ref2 - ref).max() > 0.1
+    assert np.abs(s2.cpu().numpy().reshape(-1) - ref2).max() < TOL
 
 
 @pytest.mark.parametrize('impl', ['simt', 'tc'])
@@ -158,3 +160,25 @@ def test_deform_mesh_dropin(cuda_device):
                       lat_rep_shape=torch.from_numpy(d['latent_id']).to(cuda_device).reshape(1, 1, -1))
     assert np.abs(np.asarray(out.vertices) - (d['points'] + d['offsets'])).max() < 2e-5
     assert np.array_equal(np.asarray(out.faces), mesh.faces)
+
+
+def test_tensor_core_operand_plumbing(cuda_device):
+    """D = A * B^T through the tcgen05 operand path (fp16 hi/lo split, A in TMEM, B slabs in shared memory)."""
+    import ctypes
+    from nphm_b200 import _native
+    lib = _native.lib()
+    lib.nphm_debug_tc_mma.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.RandomState(0)
+    for n, ks in ((112, 13), (208, 7), (208, 13), (16, 1)):
+        a = (rng.randn(128, 16 * ks) * 3).astype(np.float32)
+        b = (rng.randn(n, 16 * ks) * 0.1).astype(np.float32)
+        ref = a.astype(np.float64) @ b.astype(np.float64).T
+        ad, bd = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
+        errs = {}
+        for variant in range(4):
+            d = torch.zeros(128, n, device=cuda_device)
+            _native.check(lib.nphm_debug_tc_mma(ad.data_ptr(), bd.data_ptr(), n, ks, variant, d.data_ptr(), None))
+            errs[variant] = float(np.abs(d.cpu().numpy() - ref).max())
+        print('tc operand self-test n=%d ks=%d: max abs err by layout variant %s' % (n, ks, errs))
+        assert errs[0] < 2e-5 * max(1.0, np.abs(ref).max()), errs
