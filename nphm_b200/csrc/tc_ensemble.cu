@@ -42,14 +42,15 @@ constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3By
 constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
 constexpr int kColD = 0, kColAhi = 208, kColAlo = 312, kTmemCols = 512;
 // per-(query, member) record, in floats
-constexpr int kRecL0 = 0;          // 200 x float4 (W0x row, S*v0)
-constexpr int kRecB1 = 800;        // 112
-constexpr int kRecB2 = 912;        // 208
-constexpr int kRecB3 = 1120;       // 208
-constexpr int kRecW4 = 1328;       // 208
-constexpr int kRecMisc = 1536;     // b4, ax, ay, az, has_anchor, mirror, -, -
-constexpr int kRecFloats = 1544;
-constexpr int kEpiWarps = 8;
+constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
+constexpr int kRecB1 = 832;        // 112
+constexpr int kRecB2 = 944;        // 208
+constexpr int kRecB3 = 1152;       // 208
+constexpr int kRecW4 = 1360;       // 208
+constexpr int kRecMisc = 1568;     // b4, ax, ay, az, has_anchor, mirror, -, -
+constexpr int kRecFloats = 1576;
+constexpr int kEpiWarps = 16;      // 4 lane quarters x 4 column groups (8-column chunks dealt round-robin)
+constexpr int kParts = kEpiWarps / 4;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
 constexpr float kS = 144.26950408889634f;            // 100 * log2(e)
 
@@ -149,10 +150,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-struct __align__(1024) Smem {
+struct __align__(128) Smem {
     uint8_t slabs[kSlots][kSlabBytes];
     float rec[2][kRecFloats];
-    float partial[128];
+    float partial[kParts - 1][128];
     uint64_t slab_full[kSlots], slab_empty[kSlots];
     uint64_t rec_full[2], rec_empty[2];
     uint64_t a_ready, d_ready;
@@ -193,8 +194,8 @@ __device__ __forceinline__ void init_d8(uint32_t tmem_lane_base, int col, const 
 
 __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p)
 {
-    extern __shared__ uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tiles_per_query = (p.n_points + 127) / 128;
     const long long n_tiles = tiles_per_query * p.n_queries;
@@ -279,7 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         }
     } else {
         // =========================================================================== compute / epilogue warps
-        const int q = warp & 3, hsel = warp >> 2;
+        // thread = (point row, column group): warp w serves TMEM lanes 32*(w&3).. and the 8-column chunks
+        // c = part, part+4, ...  of every layer.  A chunk is always read, re-initialised and converted by the same
+        // thread, so the only cross-warp exchange is the final dot-product reduction.
+        const int q = warp & 3, part = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
         int rslot = 0;
@@ -304,82 +308,74 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
             for (int m = 0; m < p.n_members; ++m) {
                 mbar_wait(&sm.rec_full[rslot], rph);
                 const float *rec = sm.rec[rslot];
-                const float b4 = rec[kRecMisc + 0];
                 const float ax = rec[kRecMisc + 1], ay = rec[kRecMisc + 2], az = rec[kRecMisc + 3];
-                const bool has_anchor = rec[kRecMisc + 4] != 0.f, mirror = rec[kRecMisc + 5] != 0.f;
                 float cx = x - ax, cy = y - ay, cz = z - az;
-                if (mirror) cx = -cx;
+                if (rec[kRecMisc + 5] != 0.f) cx = -cx;          // mirrored member
                 cx *= kS; cy *= kS; cz *= kS;                   // coordinates in log2 units
 
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1; D preloaded with S*b1
-#pragma unroll
-                for (int c = 0; c < 7; ++c) init_d8(tl, hsel * 56 + c * 8, rec + kRecB1);
                 {
                     const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
 #pragma unroll 1
-                    for (int c = 0; c < 13; ++c) {
-                        const int n0 = hsel * 104 + c * 8;
+                    for (int c = part; c < 26; c += kParts) {
+                        const int n0 = c * 8;
                         float v[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const int n = n0 + e;
-                            if (n < kH) {
-                                const float4 w = l0[n];
-                                v[e] = sp_t(fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w))));
-                            } else {
-                                v[e] = 0.f;
-                            }
+                            const float4 w = l0[n0 + e];         // rows >= 200 are zero: sp(0) meets zero weights
+                            v[e] = sp_t(fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w))));
+                        }
+                        store_a8(tl, n0, v);
+                        if (c < 14) init_d8(tl, n0, rec + kRecB1);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a_ready);
+
+                // ---------------- epilogue of layer 1 (N = 101 -> K of layer 2 = [h1, c, 0...]); D <- S*v2
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = part; c < 26; c += kParts) {
+                    const int n0 = c * 8;
+                    if (c < 14) {
+                        float v[8];
+                        if (c < 13) {
+                            uint32_t r[8];
+                            tc_ld8(tl + kColD + n0, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = sp_t(__uint_as_float(r[e]));
+                            if (c == 12) { v[5] = cx; v[6] = cy; v[7] = cz; }       // k = 101..103: local coordinates
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = 0.f;                 // k = 104..111: padding
                         }
                         store_a8(tl, n0, v);
                     }
+                    init_d8(tl, n0, rec + kRecB2);
                 }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.a_ready);
 
-                // ---------------- epilogue of layer 1 (N = 101 -> K of layer 2 = [h1, c, 0...])
+                // ---------------- epilogue of layer 2; D <- S*b3
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < 7; ++c) {
-                    const int n0 = hsel * 56 + c * 8;
+                for (int c = part; c < 26; c += kParts) {
+                    const int n0 = c * 8;
                     uint32_t r[8];
                     tc_ld8(tl + kColD + n0, r);
                     tc_wait_ld();
                     float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int n = n0 + e;
-                        v[e] = n < kN1 ? sp_t(__uint_as_float(r[e]))
-                                       : (n == kN1 ? cx : (n == kN1 + 1 ? cy : (n == kN1 + 2 ? cz : 0.f)));
-                    }
-                    store_a8(tl, n0, v);
-                }
-                // D for layer 2: columns this thread has just read, plus columns nobody reads in layer 1
-#pragma unroll
-                for (int c = 0; c < 7; ++c) init_d8(tl, hsel * 56 + c * 8, rec + kRecB2);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) init_d8(tl, 112 + hsel * 48 + c * 8, rec + kRecB2);
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.a_ready);
-
-                // ---------------- epilogue of layer 2
-                mbar_wait(&sm.d_ready, d_ph);
-                d_ph ^= 1;
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 13; ++c) {
-                    const int n0 = hsel * 104 + c * 8;
-                    uint32_t r[8];
-                    tc_ld8(tl + kColD + n0, r);
-                    tc_wait_ld();
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = (n0 + e) < kH ? sp_t(__uint_as_float(r[e])) : 0.f;
+                    for (int e = 0; e < 8; ++e) v[e] = sp_t(__uint_as_float(r[e]));
                     store_a8(tl, n0, v);
                     init_d8(tl, n0, rec + kRecB3);
                 }
@@ -394,8 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 tc_fence_after();
                 float acc = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < 13; ++c) {
-                    const int n0 = hsel * 104 + c * 8;
+                for (int c = part; c < 26; c += kParts) {
+                    const int n0 = c * 8;
                     uint32_t r[8];
                     tc_ld8(tl + kColD + n0, r);
                     tc_wait_ld();
@@ -403,17 +399,18 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     const float4 w1 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0 + 4);
                     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (n0 + e < kH) acc = fmaf(sp_t(__uint_as_float(r[e])), w[e], acc);
+                    for (int e = 0; e < 8; ++e) acc = fmaf(sp_t(__uint_as_float(r[e])), w[e], acc);   // w4 pad = 0
                 }
-                if (hsel == 1) sm.partial[row] = acc;
+                if (part != 0) sm.partial[part - 1][row] = acc;
                 tc_fence_before();
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // the two warps of this lane quarter
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");   // the warps of this lane quarter
                 tc_fence_after();
-                if (hsel == 0) {
-                    const float s = acc + sm.partial[row] + b4;
+                if (part == 0) {
+                    float s = acc + rec[kRecMisc + 0];
+#pragma unroll
+                    for (int i = 0; i < kParts - 1; ++i) s += sm.partial[i][row];
                     float d;
-                    if (has_anchor) {
+                    if (rec[kRecMisc + 4] != 0.f) {
                         const float dx = ax - x, dy = ay - y, dz = az - z;
                         const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
                         d = -(nrm * nrm);
@@ -428,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 if (lane == 0) mbar_arrive(&sm.rec_empty[rslot]);
                 if (++rslot == 2) { rslot = 0; rph ^= 1; }
             }
-            if (hsel == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
+            if (part == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
         }
     }
 
@@ -492,12 +489,13 @@ __global__ void records_kernel(const float *__restrict__ cvec, int cvec_stride, 
     const float *cv = cvec + ((size_t)qi * n_members + m) * cvec_stride;
     float *rec = recs + ((size_t)qi * n_members + m) * kRecFloats;
     const int d_in = 3 + kCond;
-    for (int n = threadIdx.x; n < kH; n += blockDim.x) {
-        const float *w = W0 + ((size_t)set * kH + n) * d_in;
-        rec[kRecL0 + 4 * n + 0] = w[0];
-        rec[kRecL0 + 4 * n + 1] = w[1];
-        rec[kRecL0 + 4 * n + 2] = w[2];
-        rec[kRecL0 + 4 * n + 3] = kS * cv[coff[0] + n];
+    for (int n = threadIdx.x; n < kNP2; n += blockDim.x) {
+        const float *w = W0 + ((size_t)set * kH + (n < kH ? n : 0)) * d_in;
+        const bool real = n < kH;
+        rec[kRecL0 + 4 * n + 0] = real ? w[0] : 0.f;
+        rec[kRecL0 + 4 * n + 1] = real ? w[1] : 0.f;
+        rec[kRecL0 + 4 * n + 2] = real ? w[2] : 0.f;
+        rec[kRecL0 + 4 * n + 3] = real ? kS * cv[coff[0] + n] : 0.f;
     }
     for (int n = threadIdx.x; n < kNP1; n += blockDim.x) rec[kRecB1 + n] = n < kN1 ? kS * cv[coff[1] + n] : 0.f;
     for (int n = threadIdx.x; n < kNP2; n += blockDim.x) {
@@ -648,7 +646,7 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
     const long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;
     const int grid_x = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    const int smem = (int)sizeof(tc::Smem) + 1024;
+    const int smem = (int)sizeof(tc::Smem);
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::ensemble_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     tc::ensemble_tc_kernel<<<grid_x, tc::kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
