@@ -1,7 +1,476 @@
-// placeholder until the fused fitting step lands
+// Fused identity-space fitting step (no autograd graph): one iteration of
+//   inference_identity_space   reference src/NPHM/models/fitting.py:197-279
+// = ensemble forward on the sampled observation points, mean clamped |sdf| + latent regularisers, analytic gradient
+//   with respect to the latent code, torch.optim.Adam update (fitting.py:193, torch/optim/adam.py single-tensor path).
+//
+// Gradient routes (SURVEY.md 8a''):  (i) member inputs u_k = [z_glob | z_k];  (ii) anchors a = mlp_pos(z_glob) + mean,
+// which enter the local coordinates c_k = x - a_k and the blend weights w_k;  (iii) the regularisers.
+// Because u_k is constant over the points of a call, the input gradients of the two layers that see it reduce to
+//     g_u = W0u^T (sum_p delta0_p) + W2u^T (sum_p delta2_p) / sqrt(2),      g_c likewise with the xyz columns,
+// so the per-point backward only has to produce the per-member sums of the layer deltas.
+//
+// Kernels (fp32 FFMA; the step is latency bound: 5 x 1000 points):
+//   fit_member_kernel<fwd>  one CTA per (64-point tile, member): forward, s_k -> global
+//   fit_blend_kernel        per point: blend, |sdf| clamp, kept count / sum
+//   fit_member_kernel<bwd>  forward again with all activations resident in shared memory (199 KB), backward in place,
+//                           per-member delta sums and blend-path anchor gradients -> atomics
+//   fit_member_grad_kernel  per member: delta sums -> g_u, g_c -> latent / anchor gradients
+//   fit_finalize_kernel     mlp_pos forward/backward, regularisers, loss terms, Adam
 #include "engine.cuh"
+#include "simt_layers.cuh"
+#include <cmath>
+
+namespace nphm {
+namespace fit {
+
+constexpr int TM = 2;
+constexpr int P = 32 * TM;
+constexpr int kThreads = 256;
+
+struct Dims {
+    int n_members, n_symm, n_loc;
+    int H, N1, C, G, Lc;            // hidden, layer-1 width, cond width, lat_glob, lat_loc
+    int lat_dim, pos_hid;
+    int cvec_stride, coff[5];
+    // shared-memory rows
+    int r_c, r_h0, r_h1, r_h2, r_h3, r_s, rows;
+};
+
+struct Weights {
+    const float *W[5];              // reference layout [set][out][in]
+    const float *Wt[5];             // forward layout [set][K][Npad]
+    int Npad[5], K[5];
+    const float *pos_w[3], *pos_b[3], *mean_anchors;
+};
+
+struct Buffers {
+    const float *points;            // n x 3
+    long long n;
+    const float *anchors;           // n_loc x 3
+    const float *cvec;              // [members][cvec_stride]
+    float *member_s;                // n x members
+    float *out, *S, *gsign;         // n each
+    float *acc;                     // members x 2H   (sum delta0 | sum delta2)
+    float *blend_acc;               // n_loc x 3
+    float *stats;                   // [count, sum |sdf| kept, -, -]
+    float *ganch;                   // n_loc x 3
+    float *grad;                    // lat_dim
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, const Weights w, const Buffers b,
+                                                                 float lambda_surface)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads / 32;
+    const int m = blockIdx.y;
+    const long long p0 = (long long)blockIdx.x * P;
+    const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
+    const bool has_anchor = m < d.n_loc;
+    const bool mirror = (m & 1) && m < 2 * d.n_symm;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (has_anchor) { ax = b.anchors[m * 3]; ay = b.anchors[m * 3 + 1]; az = b.anchors[m * 3 + 2]; }
+
+    float x[TM], y[TM], z[TM];
+    bool valid[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long idx = p0 + lane * TM + i;
+        valid[i] = idx < b.n;
+        const float *pp = b.points + (valid[i] ? idx : 0) * 3;
+        x[i] = pp[0]; y[i] = pp[1]; z[i] = pp[2];
+    }
+    float *rc = sm + (size_t)d.r_c * P, *rh0 = sm + (size_t)d.r_h0 * P, *rh1 = sm + (size_t)d.r_h1 * P;
+    float *rh2 = sm + (size_t)d.r_h2 * P, *rh3 = sm + (size_t)d.r_h3 * P, *rs = sm + (size_t)d.r_s * P;
+    if (warp == 0) {
+        float cx[TM], cy[TM], cz[TM];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            cx[i] = x[i] - ax; cy[i] = y[i] - ay; cz[i] = z[i] - az;
+            if (mirror) cx[i] = -cx[i];
+        }
+        store_act<TM>(rc + 0 * P + lane * TM, cx); store_act<TM>(rc + 1 * P + lane * TM, cy); store_act<TM>(rc + 2 * P + lane * TM, cz);
+        float *skip = rh1 + (size_t)d.N1 * P;       // rows N1..N1+2 of the skip layer input
+        store_act<TM>(skip + 0 * P + lane * TM, cx); store_act<TM>(skip + 1 * P + lane * TM, cy); store_act<TM>(skip + 2 * P + lane * TM, cz);
+    }
+    __syncthreads();
+    const float *cv = b.cvec + (size_t)m * d.cvec_stride;
+    FoldedLayer L[5];
+    const int Ns[5] = {d.H, d.N1, d.H, d.H, 1};
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+        L[l] = FoldedLayer{w.Wt[l] + (size_t)set * w.K[l] * w.Npad[l], w.K[l], Ns[l], w.Npad[l], d.coff[l], l < 4 ? 1 : 0};
+    dense_layer<TM>(L[0], L[0].Wt, cv + L[0].coff, rc, rh0, warp, lane, nwarps);
+    __syncthreads();
+    dense_layer<TM>(L[1], L[1].Wt, cv + L[1].coff, rh0, rh1, warp, lane, nwarps);
+    __syncthreads();
+    dense_layer<TM>(L[2], L[2].Wt, cv + L[2].coff, rh1, rh2, warp, lane, nwarps);
+    __syncthreads();
+    dense_layer<TM>(L[3], L[3].Wt, cv + L[3].coff, rh2, rh3, warp, lane, nwarps);
+    __syncthreads();
+    narrow_layer<TM>(L[4], L[4].Wt, cv + L[4].coff, rh3, rs, warp, lane, nwarps);
+    __syncthreads();
+
+    if (!BWD) {
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const long long idx = p0 + lane * TM + i;
+                if (valid[i]) b.member_s[idx * d.n_members + m] = rs[lane * TM + i];
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ backward
+    // upstream: g_s = g_out * w_k / (S + 1e-6),   g_out = lambda_surface * sign(sdf) * kept / n_kept
+    const float inv_count = 1.0f / b.stats[0];
+    float gs[TM];
+    float ba[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long idx = p0 + lane * TM + i;
+        gs[i] = 0.f;
+        if (valid[i]) {
+            const float g_out = lambda_surface * b.gsign[idx] * inv_count;
+            const float Sp = b.S[idx] + 1e-6f;
+            float dd, r = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            if (has_anchor) {
+                dx = ax - x[i]; dy = ay - y[i]; dz = az - z[i];
+                r = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float nrm = r + 10e-6f;
+                dd = -(nrm * nrm);
+            } else {
+                dd = -0.2f;
+            }
+            const float wk = expf(__fdiv_rn(dd, 0.01f));
+            gs[i] = g_out * wk / Sp;
+            if (has_anchor && warp == 0 && r > 0.f) {
+                // blend path: d out / d w_k = (s_k - out) / (S + eps);  d w_k / d a_k = w_k/0.01 * (-2)(r + 1e-5) (a - x)/r
+                const float s_k = rs[lane * TM + i];
+                const float g_w = g_out * (s_k - b.out[idx]) / Sp;
+                const float coef = g_w * wk * (1.0f / 0.01f) * (-2.0f) * (r + 10e-6f) / r;
+                ba[0] += coef * dx; ba[1] += coef * dy; ba[2] += coef * dz;
+            }
+        }
+    }
+    if (has_anchor && warp == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = ba[a];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v != 0.f) atomicAdd(b.blend_acc + m * 3 + a, v);
+        }
+    }
+    // delta3 = g_s * w4 * sigma'(h3), in place over h3
+    {
+        const float *W4 = w.W[4] + (size_t)set * d.H;
+        for (int n = warp; n < d.H; n += nwarps) {
+            float *ptr = rh3 + (size_t)n * P + lane * TM;
+            float h[TM], o[TM];
+            load_act<TM>(ptr, h);
+            const float w4 = __ldg(W4 + n);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) o[i] = gs[i] * w4 * (h[i] > 0.2f ? 1.0f : -expm1f(-100.0f * h[i]));
+            store_act<TM>(ptr, o);
+        }
+    }
+    __syncthreads();
+    dense_layer_bwd<TM>(w.W[3] + (size_t)set * d.H * d.H, d.H, d.H, d.H, 1.0f, rh3, rh2, warp, lane, nwarps);     // delta2
+    __syncthreads();
+    dense_layer_bwd<TM>(w.W[2] + (size_t)set * d.H * d.H, d.H, d.H, d.N1, 0.70710678118654752f, rh2, rh1, warp, lane, nwarps);   // delta1
+    __syncthreads();
+    dense_layer_bwd<TM>(w.W[1] + (size_t)set * d.N1 * d.H, d.H, d.N1, d.H, 1.0f, rh1, rh0, warp, lane, nwarps);    // delta0
+    __syncthreads();
+    // per-member sums over the points of the tile
+    float *acc = b.acc + (size_t)m * 2 * d.H;
+    for (int n = warp; n < 2 * d.H; n += nwarps) {
+        const float *row = (n < d.H ? rh0 + (size_t)n * P : rh2 + (size_t)(n - d.H) * P) + lane * TM;
+        float v[TM];
+        load_act<TM>(row, v);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) s += v[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s != 0.f) atomicAdd(acc + n, s);
+    }
+}
+
+// sdf = sum_k w_k s_k / (sum_k w_k + 1e-6); kept = |sdf| < clamp   (fitting.py:234-246)
+__global__ void fit_blend_kernel(const Dims d, const Buffers b, float clamp)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float cnt = 0.f, sum = 0.f;
+    if (idx < b.n) {
+        const float x = b.points[idx * 3], y = b.points[idx * 3 + 1], z = b.points[idx * 3 + 2];
+        float num = 0.f, den = 0.f;
+        for (int k = 0; k < d.n_members; ++k) {
+            float dd;
+            if (k < d.n_loc) {
+                const float dx = b.anchors[k * 3] - x, dy = b.anchors[k * 3 + 1] - y, dz = b.anchors[k * 3 + 2] - z;
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                dd = -(nrm * nrm);
+            } else {
+                dd = -0.2f;
+            }
+            const float wk = expf(__fdiv_rn(dd, 0.01f));
+            num = fmaf(wk, b.member_s[idx * d.n_members + k], num);
+            den += wk;
+        }
+        const float out = __fdiv_rn(num, den + 1e-6f);
+        const float l = fabsf(out);
+        const bool kept = l < clamp;
+        b.out[idx] = out; b.S[idx] = den;
+        b.gsign[idx] = kept ? (out > 0.f ? 1.f : (out < 0.f ? -1.f : 0.f)) : 0.f;
+        if (kept) { cnt = 1.f; sum = l; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt != 0.f) { atomicAdd(b.stats + 0, cnt); atomicAdd(b.stats + 1, sum); }
+}
+
+// per member: g_u = W0u^T D0 + W2u^T D2 / sqrt2 ; g_c = W0x^T D0 + W2x^T D2 / sqrt2
+__global__ void fit_member_grad_kernel(const Dims d, const Weights w, const Buffers b)
+{
+    const int m = blockIdx.x;
+    const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
+    const float *D0 = b.acc + (size_t)m * 2 * d.H, *D2 = D0 + d.H;
+    const int in0 = 3 + d.C, in2 = d.H;                 // row lengths of W0 / W2 in the reference layout
+    const float *W0 = w.W[0] + (size_t)set * d.H * in0;
+    const float *W2 = w.W[2] + (size_t)set * d.H * in2;
+    const float r2 = 0.70710678118654752f;
+    __shared__ float gc[3];
+    for (int j = threadIdx.x; j < 3 + d.C; j += blockDim.x) {
+        // j < 3: xyz columns; j >= 3: condition columns.  In W2 the order is [h1 (N1) | xyz (3) | cond (C)].
+        float s0 = 0.f, s2 = 0.f;
+        for (int n = 0; n < d.H; ++n) {
+            s0 = fmaf(W0[(size_t)n * in0 + j], D0[n], s0);
+            s2 = fmaf(W2[(size_t)n * in2 + d.N1 + j], D2[n], s2);
+        }
+        const float g = s0 + r2 * s2;
+        if (j < 3) gc[j] = g;
+        else {
+            const int u = j - 3;
+            if (u < d.G) atomicAdd(b.grad + u, g);
+            else b.grad[d.G + m * d.Lc + (u - d.G)] = g;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && m < d.n_loc) {
+        const bool mirror = (m & 1) && m < 2 * d.n_symm;
+        // c = x - a (x component negated for mirrored members)  =>  d c / d a = -1 (+1 for the mirrored x)
+        const float sign = (threadIdx.x == 0 && mirror) ? 1.0f : -1.0f;
+        b.ganch[m * 3 + threadIdx.x] = b.blend_acc[m * 3 + threadIdx.x] + sign * gc[threadIdx.x];
+    }
+}
+
+struct FinalizeArgs {
+    float lambda_surface, lambda_reg_global, lambda_reg_loc, lambda_reg_unobserved, lambda_symm_dist;
+    float step_size, bc2_sqrt, one_minus_beta1, beta2, one_minus_beta2, eps;
+    int apply_update;
+};
+
+// mlp_pos backward (anchor gradient -> z_glob), regularisers (fitting.py:252-268), loss terms, Adam
+__global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const Weights w, const Buffers b, float *latent,
+                                                           float *adam_m, float *adam_v, const FinalizeArgs a,
+                                                           float *loss_terms, float *grad_out)
+{
+    extern __shared__ float sh[];
+    float *h0 = sh, *h1 = h0 + d.pos_hid, *g1 = h1 + d.pos_hid, *g0 = g1 + d.pos_hid, *red = g0 + d.pos_hid;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int Hd = d.pos_hid, G = d.G, O = d.n_loc * 3;
+    // forward of mlp_pos (ReLU masks)
+    for (int n = tid; n < Hd; n += nt) {
+        float s = w.pos_b[0][n];
+        for (int j = 0; j < G; ++j) s = fmaf(w.pos_w[0][(size_t)n * G + j], latent[j], s);
+        h0[n] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int n = tid; n < Hd; n += nt) {
+        float s = w.pos_b[1][n];
+        for (int j = 0; j < Hd; ++j) s = fmaf(w.pos_w[1][(size_t)n * Hd + j], h0[j], s);
+        h1[n] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    // backward
+    for (int j = tid; j < Hd; j += nt) {
+        float s = 0.f;
+        for (int o = 0; o < O; ++o) s = fmaf(w.pos_w[2][(size_t)o * Hd + j], b.ganch[o], s);
+        g1[j] = h1[j] > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    for (int j = tid; j < Hd; j += nt) {
+        float s = 0.f;
+        for (int n = 0; n < Hd; ++n) s = fmaf(w.pos_w[1][(size_t)n * Hd + j], g1[n], s);
+        g0[j] = h0[j] > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    for (int j = tid; j < G; j += nt) {
+        float s = 0.f;
+        for (int n = 0; n < Hd; ++n) s = fmaf(w.pos_w[0][(size_t)n * G + j], g0[n], s);
+        b.grad[j] += s;
+    }
+    __syncthreads();
+    // regularisers
+    float part[4] = {0.f, 0.f, 0.f, 0.f};        // reg_global, reg_loc, reg_unobserved, (unused)
+    const int unobs[3] = {30, 31, 39};
+    for (int j = tid; j < d.lat_dim; j += nt) {
+        const float zj = latent[j];
+        float g = 0.f;
+        if (j < G) { part[0] += zj * zj; g += a.lambda_reg_global * 2.f * zj; }
+        else {
+            part[1] += zj * zj; g += a.lambda_reg_loc * 2.f * zj;
+            const int k = (j - G) / d.Lc;
+            if (k == unobs[0] || k == unobs[1] || k == unobs[2]) { part[2] += zj * zj; g += a.lambda_reg_unobserved * 2.f * zj; }
+        }
+        b.grad[j] += g;
+    }
+    for (int i = 0; i < 3; ++i) {
+        float v = part[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[i * 8 + (tid >> 5)] = v;
+    }
+    __syncthreads();
+    // symmetric-pair distance: mean_i ||z_2i - z_2i+1||  (one warp per pair)
+    float symm_local = 0.f;
+    for (int pair = tid >> 5; pair < d.n_symm; pair += nt >> 5) {
+        const float *za = latent + G + (2 * pair) * d.Lc, *zb = za + d.Lc;
+        float ss = 0.f;
+        for (int j = tid & 31; j < d.Lc; j += 32) { const float df = za[j] - zb[j]; ss += df * df; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float nrm = sqrtf(ss);
+        if (nrm > 0.f) {
+            for (int j = tid & 31; j < d.Lc; j += 32) {
+                const float g = a.lambda_symm_dist * (za[j] - zb[j]) / (nrm * d.n_symm);
+                b.grad[G + (2 * pair) * d.Lc + j] += g;
+                b.grad[G + (2 * pair + 1) * d.Lc + j] -= g;
+            }
+        }
+        if ((tid & 31) == 0) symm_local += nrm;
+    }
+    if ((tid & 31) == 0) red[24 + (tid >> 5)] = symm_local;
+    __syncthreads();
+    if (tid == 0 && loss_terms) {
+        float rg = 0.f, rl = 0.f, ru = 0.f, sy = 0.f;
+        for (int wi = 0; wi < nt / 32; ++wi) { rg += red[wi]; rl += red[8 + wi]; ru += red[16 + wi]; sy += red[24 + wi]; }
+        loss_terms[0] = b.stats[1] / b.stats[0];      // surface = mean |sdf| over kept points (NaN if none, like torch)
+        loss_terms[1] = rg; loss_terms[2] = rl; loss_terms[3] = ru;
+        loss_terms[4] = d.n_symm ? sy / d.n_symm : 0.f;
+        loss_terms[5] = b.stats[0];
+    }
+    __syncthreads();
+    // Adam (torch 2.x single-tensor update order)
+    for (int j = tid; j < d.lat_dim; j += nt) {
+        const float g = b.grad[j];
+        if (grad_out) grad_out[j] = g;
+        if (a.apply_update) {
+            float mm = adam_m[j], vv = adam_v[j];
+            mm = mm + (g - mm) * a.one_minus_beta1;                 // exp_avg.lerp_(grad, 1 - beta1)
+            vv = vv * a.beta2 + a.one_minus_beta2 * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            const float denom = sqrtf(vv) / a.bc2_sqrt + a.eps;
+            latent[j] = latent[j] - a.step_size * (mm / denom);     // param.addcdiv_(exp_avg, denom, value=-step_size)
+            adam_m[j] = mm; adam_v[j] = vv;
+        }
+    }
+}
+
+}  // namespace fit
+}  // namespace nphm
+
 using namespace nphm;
-extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *, long long) { return 0; }
-extern "C" int nphm_fit_identity_step(nphm_ensemble *, const float *, long long, float *, float *, float *,
-                                      const nphm_fit_params *, int, float *, float *, void *, void *)
-{ set_error("fit step not built"); return NPHM_ERR_UNSUPPORTED; }
+
+extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long n_points)
+{
+    if (!h || n_points < 0) return -1;
+    const long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
+                             (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
+    return floats * 4 + 1024;
+}
+
+extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
+                                      float *adam_m_dev, float *adam_v_dev, const nphm_fit_params *fp, int apply_update,
+                                      float *loss_terms_dev, float *grad_out_dev, void *workspace_dev, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(h && h->loaded, "nphm_fit_identity_step: weights not loaded");
+    NPHM_REQUIRE(points_dev && latent_dev && fp && n_points > 0, "nphm_fit_identity_step: NULL argument or no points");
+    NPHM_REQUIRE(!apply_update || (adam_m_dev && adam_v_dev), "nphm_fit_identity_step: Adam state is NULL");
+    if (h->dims.n_lin != 5 || h->dims.skip != 2) {
+        set_error("nphm_fit_identity_step: only ensembles with 4 hidden layers are supported");
+        return NPHM_ERR_UNSUPPORTED;
+    }
+    fit::Dims d{};
+    d.n_members = h->n_members; d.n_symm = h->cfg.n_symm_pairs; d.n_loc = h->cfg.n_loc;
+    d.H = h->cfg.hidden_dim; d.N1 = h->dims.N[1]; d.C = h->dims.cond_dim; d.G = h->cfg.lat_dim_glob; d.Lc = h->cfg.lat_dim_loc;
+    d.lat_dim = h->lat_dim; d.pos_hid = h->cfg.pos_mlp_dim; d.cvec_stride = h->dims.cvec_stride;
+    for (int l = 0; l < 5; ++l) d.coff[l] = h->dims.coff[l];
+    d.r_c = 0; d.r_h0 = 3; d.r_h1 = d.r_h0 + d.H; d.r_h2 = d.r_h1 + d.N1 + 3; d.r_h3 = d.r_h2 + d.H; d.r_s = d.r_h3 + d.H;
+    d.rows = d.r_s + 8 + 8 * (fit::kThreads / 32);
+    const size_t smem = (size_t)d.rows * fit::P * sizeof(float);
+    if (smem > 227 * 1024) {
+        set_error("nphm_fit_identity_step: hidden width %d too large for the fitting kernel", d.H);
+        return NPHM_ERR_UNSUPPORTED;
+    }
+    fit::Weights w{};
+    for (int l = 0; l < 5; ++l) {
+        w.W[l] = h->weights.W[l].as<float>(); w.Wt[l] = h->weights.Wt[l].as<float>();
+        w.Npad[l] = h->dims.Npad[l]; w.K[l] = h->dims.K[l];
+    }
+    for (int i = 0; i < 3; ++i) { w.pos_w[i] = h->pos_w[i].as<float>(); w.pos_b[i] = h->pos_b[i].as<float>(); }
+    w.mean_anchors = h->mean_anchors.as<float>();
+
+    int rc;
+    float *ws = static_cast<float *>(workspace_dev);
+    if (!ws) {
+        if ((rc = h->fit_scratch.reserve((size_t)nphm_fit_workspace_bytes(h, n_points)))) return rc;
+        ws = h->fit_scratch.as<float>();
+    }
+    if ((rc = ensemble_prepare(h, latent_dev, 1, stream))) return rc;      // anchors + folded constants
+    fit::Buffers b{};
+    b.points = points_dev; b.n = n_points; b.anchors = h->anchors.as<float>(); b.cvec = h->cvec.as<float>();
+    float *p = ws;
+    b.member_s = p; p += n_points * h->n_members;
+    b.out = p; p += n_points; b.S = p; p += n_points; b.gsign = p; p += n_points;
+    float *zero_begin = p;
+    b.acc = p; p += (size_t)h->n_members * 2 * d.H;
+    b.blend_acc = p; p += d.n_loc * 3;
+    b.stats = p; p += 8;
+    b.ganch = p; p += d.n_loc * 3;
+    b.grad = p; p += d.lat_dim;
+    NPHM_CUDA_CHECK(cudaMemsetAsync(zero_begin, 0, (size_t)(p - zero_begin) * sizeof(float), stream));
+
+    const int tiles = (int)ceil_div(n_points, fit::P);
+    dim3 grid(tiles, h->n_members);
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_member_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_member_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fit::fit_member_kernel<false><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    fit::fit_member_grad_kernel<<<h->n_members, 128, 0, stream>>>(d, w, b);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+
+    fit::FinalizeArgs a{};
+    a.lambda_surface = fp->lambda_surface; a.lambda_reg_global = fp->lambda_reg_global; a.lambda_reg_loc = fp->lambda_reg_loc;
+    a.lambda_reg_unobserved = fp->lambda_reg_unobserved; a.lambda_symm_dist = fp->lambda_symm_dist;
+    const double beta1 = 0.9, beta2 = 0.999;
+    const int step = fp->step > 0 ? fp->step : 1;
+    const double bc1 = 1.0 - std::pow(beta1, step), bc2 = 1.0 - std::pow(beta2, step);
+    a.step_size = (float)((double)fp->lr / bc1);
+    a.bc2_sqrt = (float)std::sqrt(bc2);
+    a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
+    a.eps = 1e-8f; a.apply_update = apply_update;
+    const size_t fsm = (size_t)(4 * d.pos_hid + 64) * sizeof(float);
+    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}

@@ -1,0 +1,241 @@
+"""Drop-in mirror of the reference module ``NPHM.models.fitting``.
+
+  * ``inference_identity_space``                 src/NPHM/models/fitting.py:180-285
+  * ``inference_iterative_root_finding_joint``   src/NPHM/models/fitting.py:14-177
+
+``inference_identity_space`` runs on the fused fitting kernels (``nphm_fit_identity_step``: forward, clamped |sdf|
+loss, analytic latent gradient and Adam in five launches, no autograd graph) when the decoder is a
+``FastEnsembleDeepSDFMirrored`` on a CUDA device; otherwise it falls back to autograd through the composite modules,
+written here independently but following the same loop.  Host-side behaviour kept from the reference: the
+point sampling draws from torch's global CPU generator in the same order (``torch.randint`` at :214,:219), the
+``lambdas`` dict is mutated by the schedule (:199-206), Adam runs with lr 0.01*lr_scale halved by the schedule, and the
+returned anchors are those of the LAST iteration's pre-update latent (:211).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List
+
+import torch
+from torch import optim
+
+from .. import _native
+from .EnsembledDeepSDF import FastEnsembleDeepSDFMirrored
+from .iterative_root_finding import search, nabla          # noqa: F401  (same names as the reference imports)
+from .diff_operators import gradient, jac                    # noqa: F401
+
+NUM_OBSERVATIONS_PER_BATCH = 5
+NUM_POINTS_PER_OBSERVATION = 1000
+
+
+def _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr):
+    """Eye-balled schedule of the reference (:199-206 / :40-52): divides lr and lambdas at fixed iterations."""
+    key = int(j / step_scale)
+    if key in schedule_cfg.get('lr', {}):
+        lr = lr / schedule_cfg['lr'][key]
+    for cfg_key, lam_key in (('symm_dist', 'symm_dist'), ('reg_glob', 'reg_global'), ('reg_loc', 'reg_loc'),
+                             ('reg_expr', 'reg_expr')):
+        if cfg_key in schedule_cfg and key in schedule_cfg[cfg_key] and (lam_key in lambdas or cfg_key != 'reg_expr'):
+            lambdas[lam_key] /= schedule_cfg[cfg_key][key]
+    return lr
+
+
+def _clamp_for_iteration(j, step_scale):
+    """Sequential strict filters l<0.1, (j>250) l<0.05, (j>500) l<0.0075 collapse to one threshold (:239-246)."""
+    clamp = 0.1
+    if j > int(250 * step_scale):
+        clamp = 0.05
+    if j > int(500 * step_scale):
+        clamp = 0.0075
+    return clamp
+
+
+def _sample_observations(all_obs):
+    """Reference sampling order on the global CPU generator (:214-222)."""
+    num_observations = len(all_obs)
+    sampled_observations_idx = torch.randint(0, num_observations, [NUM_OBSERVATIONS_PER_BATCH])
+    sampled_points = []
+    for i in range(NUM_OBSERVATIONS_PER_BATCH):
+        sampled_idx = sampled_observations_idx[i]
+        n_samps = min(NUM_POINTS_PER_OBSERVATION, all_obs[sampled_idx].shape[0])
+        subsample_idx = torch.randint(0, all_obs[sampled_idx].shape[0], [n_samps])
+        sampled_points.append(all_obs[sampled_idx][subsample_idx.to(all_obs[sampled_idx].device), :])
+    return torch.stack(sampled_points, dim=0), sampled_observations_idx
+
+
+def _fused_identity(decoder) -> bool:
+    p = next(decoder.parameters())
+    return isinstance(decoder, FastEnsembleDeepSDFMirrored) and p.is_cuda and decoder.ensembled_deep_sdf.num_layers == 6
+
+
+class IdentityFitter:
+    """Stateful wrapper around ``nphm_fit_identity_step``: latent + Adam moments live on the device."""
+
+    def __init__(self, decoder: FastEnsembleDeepSDFMirrored, device):
+        self.decoder = decoder
+        self.device = device
+        self.engine = decoder.engine()
+        self.latent = torch.zeros(decoder.lat_dim, device=device, dtype=torch.float32)
+        self.m = torch.zeros_like(self.latent)
+        self.v = torch.zeros_like(self.latent)
+        self.loss_terms = torch.zeros(8, device=device, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.latent)
+        self.t = 0
+
+    def step(self, points: torch.Tensor, lambdas: Dict[str, float], clamp: float, lr: float, apply_update: bool = True):
+        pts = points.reshape(-1, 3).to(dtype=torch.float32).contiguous()
+        if apply_update:
+            self.t += 1
+        fp = _native.FitParams(float(lambdas.get('surface', 0.0)), float(lambdas.get('reg_global', 0.0)),
+                               float(lambdas.get('reg_loc', 0.0)), float(lambdas.get('reg_unobserved', 0.0)),
+                               float(lambdas.get('symm_dist', 0.0)), float(clamp), float(lr), max(self.t, 1))
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().nphm_fit_identity_step(
+                self.engine.handle, pts.data_ptr(), pts.shape[0], self.latent.data_ptr(), self.m.data_ptr(),
+                self.v.data_ptr(), ctypes.byref(fp), int(apply_update), self.loss_terms.data_ptr(),
+                self.grad.data_ptr(), None, torch.cuda.current_stream(self.device).cuda_stream),
+                'nphm_fit_identity_step')
+
+
+def inference_identity_space(decoder,
+                             all_obs: List[torch.Tensor],
+                             lambdas,
+                             n_steps,
+                             schedule_cfg: Dict,
+                             step_scale=1,
+                             lr_scale=1):
+    """Fit the identity code to point-cloud observations.  Returns ``(lat_rep_shape (1,1,D), anchors (1,K,3))``."""
+    device = all_obs[0].device
+    lr = 0.01 * lr_scale
+    if _fused_identity(decoder) and device.type == 'cuda':
+        fitter = IdentityFitter(decoder, device)
+        z_prev = fitter.latent.clone()
+        for j in range(int(n_steps * step_scale)):
+            lr = _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr)
+            obs, _ = _sample_observations(all_obs)
+            z_prev.copy_(fitter.latent)
+            fitter.step(obs, lambdas, _clamp_for_iteration(j, step_scale), lr)
+        with torch.no_grad():
+            _, anchors = fitter.engine.query(torch.zeros(1, 1, 3, device=device), z_prev.reshape(1, -1), eval_quirk=False)
+        lat_rep_shape = fitter.latent.reshape(1, 1, -1).clone().requires_grad_(True)
+        return lat_rep_shape, anchors
+
+    # ---- autograd path (any decoder, CPU or GPU)
+    lat_dim = decoder.lat_dim
+    lat_rep_shape = torch.zeros([1, 1, lat_dim], device=device, requires_grad=True)
+    opt = optim.Adam(params=[lat_rep_shape], lr=lr)
+    anchors = None
+    for j in range(int(n_steps * step_scale)):
+        new_lr = _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr)
+        if new_lr != lr:
+            lr = new_lr
+            for group in opt.param_groups:
+                group['lr'] = lr
+        opt.zero_grad()
+        _, anchors = decoder(torch.zeros([1, 1, 3], device=device), lat_rep_shape, None)
+        obs, _ = _sample_observations(all_obs)
+        nb = obs.shape[0]
+        if hasattr(decoder, 'lat_dim_loc'):
+            sdf, _ = decoder(obs, lat_rep_shape.repeat(nb, 1, 1), None)
+        else:
+            sdf, _ = decoder(obs, lat_rep_shape.repeat(nb, obs.shape[1], 1), None)
+        l = sdf.abs()
+        l = l[l < _clamp_for_iteration(j, step_scale)]
+        loss_dict = {'surface': l.mean()}
+        loss_dict.update(_latent_regularisers(decoder, lat_rep_shape))
+        loss = 0
+        for k in lambdas.keys():
+            loss = loss + loss_dict[k] * lambdas[k]
+        loss.backward()
+        opt.step()
+    return lat_rep_shape, anchors
+
+
+def _latent_regularisers(decoder, lat_rep_shape):
+    """reg_loc / reg_global / reg_unobserved / symm_dist of the reference (:252-272)."""
+    out = {}
+    if hasattr(decoder, 'lat_dim_glob'):
+        g, lc = decoder.lat_dim_glob, decoder.lat_dim_loc
+        out['reg_loc'] = (torch.norm(lat_rep_shape[..., g:], dim=-1) ** 2).mean()
+        out['reg_global'] = (torch.norm(lat_rep_shape[..., :g], dim=-1) ** 2).mean()
+        ru = 0
+        for idx in (30, 31, 39):
+            ru = ru + torch.norm(lat_rep_shape[..., g + idx * lc:g + (idx + 1) * lc], dim=-1).square().mean()
+        out['reg_unobserved'] = ru
+        n_pairs = decoder.num_symm_pairs
+        loc = lat_rep_shape[:, :, g:g + 2 * n_pairs * lc].view(lat_rep_shape.shape[0], n_pairs * 2, lc)
+        out['symm_dist'] = torch.norm(loc[:, ::2, :] - loc[:, 1::2, :], dim=-1).mean()
+    else:
+        out['symm_dist'] = 0
+        out['reg_unobserved'] = 0
+        out['reg_loc'] = 0
+        out['reg_global'] = (torch.norm(lat_rep_shape, dim=-1) ** 2).mean()
+    return out
+
+
+def inference_iterative_root_finding_joint(decoder,
+                                           decoder_expr,
+                                           all_obs: List[torch.Tensor],
+                                           lambdas,
+                                           n_steps,
+                                           schedule_cfg: Dict,
+                                           step_scale=1,
+                                           lr_scale=1):
+    """Joint identity + expression fitting with Broyden correspondences (reference :14-177).
+
+    Autograd implementation on top of the drop-in modules: the no-grad network evaluations inside the Broyden
+    search run on the fused kernels, the loss/backward part uses the composite path.  Returns
+    ``(lat_rep (n_obs,1,E), lat_rep_shape (1,1,D), anchors)``."""
+    device = all_obs[0].device
+    num_observations = len(all_obs)
+    lat_expr_dim = decoder_expr.lat_dim_expr if hasattr(decoder_expr, 'lat_dim_expr') else 200
+    lat_rep = torch.zeros([num_observations, 1, lat_expr_dim], device=device, requires_grad=True)
+    lat_rep_shape = torch.zeros([1, 1, decoder.lat_dim], device=device, requires_grad=True)
+    lr = 0.01 * lr_scale
+    opt = optim.Adam(params=[lat_rep_shape], lr=lr)
+    opt_expr = optim.Adam(params=[lat_rep], lr=lr)
+    anchors = None
+    for j in range(int(n_steps * step_scale)):
+        new_lr = _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr)
+        if new_lr != lr:
+            lr = new_lr
+            for o in (opt, opt_expr):
+                for group in o.param_groups:
+                    group['lr'] = lr
+        opt.zero_grad()
+        opt_expr.zero_grad()
+        _, anchors = decoder(torch.zeros([1, 1, 3], device=device), lat_rep_shape, None)
+        obs, obs_idx = _sample_observations(all_obs)
+        obs_idx = obs_idx.long().to(device)
+        nb, n_point, _ = obs.shape
+        glob_cond = torch.cat([lat_rep_shape.repeat(nb, 1, 1), lat_rep[obs_idx, :, :]], dim=-1)
+        has_local = hasattr(decoder, 'lat_dim_loc')
+        search_anchors = anchors.clone().unsqueeze(1).repeat(nb, n_point, 1, 1) if has_local else None
+        p_corresp, search_result = search(obs, glob_cond.repeat(1, n_point, 1), decoder_expr, search_anchors,
+                                          multi_corresp=False)
+        p_corresp = p_corresp.detach()
+        _anchors = anchors.clone().unsqueeze(1).repeat(nb, n_point, 1, 1) if anchors is not None else None
+        # implicit differentiation of the root: value(xc) = p, d xc = -J^-1 d F_ex
+        preds_posed, _ = decoder_expr(p_corresp, glob_cond.repeat(1, n_point, 1), _anchors)
+        preds_posed = preds_posed + p_corresp
+        grad_inv = jac(decoder_expr, p_corresp, glob_cond.repeat(1, n_point, 1), _anchors).inverse()
+        correction = preds_posed - preds_posed.detach()
+        correction = torch.einsum('bnij,bnj->bni', -grad_inv.detach(), correction)
+        xc = p_corresp + correction
+        if has_local:
+            sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, 1, 1), None)
+        else:
+            sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, n_point, 1), None)
+        sdf = sdf[search_result['valid_ids'], :]
+        l = sdf.abs()
+        l = l[l < _clamp_for_iteration(j, step_scale)]
+        loss_dict = {'surface': l.mean(),
+                     'reg_expr': (torch.norm(lat_rep[obs_idx, :, :], dim=-1) ** 2).mean()}
+        loss_dict.update(_latent_regularisers(decoder, lat_rep_shape))
+        loss = 0
+        for k in lambdas.keys():
+            loss = loss + loss_dict[k] * lambdas[k]
+        loss.backward()
+        opt.step()
+        opt_expr.step()
+    return lat_rep, lat_rep_shape, anchors

@@ -284,3 +284,124 @@ def mesh_from_logits(logits: np.ndarray, mini, maxi, resolution: int):
     verts = verts * np.expand_dims(step, axis=0)
     verts += [mini[0], mini[1], mini[2]]
     return verts, tris
+
+
+# --------------------------------------------------------------------------------------------------
+# identity-space fitting: loss and latent gradient (fitting.py:197-279), dense formulation, manual backprop
+# --------------------------------------------------------------------------------------------------
+def _sigmoid100(a: np.ndarray) -> np.ndarray:
+    """d softplus_100 / da as torch's backward computes it: 1 beyond the threshold, else e/(e+1)."""
+    ba = a.astype(F32) * F32(100.0)
+    with np.errstate(over='ignore'):
+        e = np.exp(np.minimum(ba, F32(30.0)))
+    return np.where(ba > F32(20.0), F32(1.0), e / (e + F32(1.0))).astype(F32)
+
+
+def fit_identity_loss_grad(p: EnsembleParams, points: np.ndarray, z: np.ndarray, lambdas: dict, clamp: float):
+    """One evaluation of the loss of ``inference_identity_space`` and its gradient w.r.t. the latent ``z``.
+
+    points: (N,3) sampled observation points (already stacked), z: (lat_dim,).  Loss terms
+    (fitting.py:239-268): surface = mean(|sdf|[|sdf| < clamp]), reg_global = |z[:64]|^2, reg_loc = |z[64:]|^2,
+    reg_unobserved = sum_{k in 30,31,39} |z_k|^2, symm_dist = mean_i |z_2i - z_2i+1|.
+    Returns (terms dict, grad (lat_dim,), n_kept)."""
+    x = np.ascontiguousarray(points, dtype=F32)
+    z = np.asarray(z, dtype=F32)
+    N = x.shape[0]
+    G, L, A, K = p.G, p.L, p.A, p.K
+    r2 = F32(np.sqrt(2))
+    # ---- anchors = mlp_pos(z_g) + mean  (forward with ReLU masks kept)
+    zg = z[:G]
+    a0 = p.pos_W[0] @ zg + p.pos_b[0]; h0 = np.maximum(a0, 0)
+    a1 = p.pos_W[1] @ h0 + p.pos_b[1]; h1 = np.maximum(a1, 0)
+    anchors = ((p.pos_W[2] @ h1 + p.pos_b[2]).reshape(K, 3) + p.mean_anchors).astype(F32)
+    # ---- per-member forward, keeping pre-activations
+    origin = np.concatenate([anchors, np.zeros((1, 3), F32)], axis=0)
+    coords = x[:, None, :] - origin[None, :, :]
+    flip = np.ones((A, 3), F32); flip[1:2 * p.n_symm:2, 0] = -1
+    coords = coords * flip[None]
+    z_loc = z[G:].reshape(A, L)
+    cond = np.concatenate([np.broadcast_to(zg, (A, G)), z_loc], axis=1)
+    saved = []
+    s = np.empty((N, A), F32)
+    for k in range(A):
+        ws = p.ws[k]
+        inp = np.concatenate([coords[:, k, :], np.broadcast_to(cond[k], (N, G + L))], axis=1).astype(F32)
+        pre = []
+        h = inp
+        for layer in range(p.n_lin):
+            if layer == p.skip:
+                h = (np.concatenate([h, inp], axis=1) / r2).astype(F32)
+            a = h @ p.W[layer][ws].T + p.b[layer][ws]
+            pre.append((h, a))
+            h = softplus100(a) if layer < p.n_lin - 1 else a
+        s[:, k] = h[:, 0]
+        saved.append((inp, pre))
+    # ---- blend
+    diff = anchors[None] - x[:, None, :]
+    r = np.sqrt((diff * diff).sum(axis=2)).astype(F32)
+    nrm = r + F32(10e-6)
+    dist = np.concatenate([-(nrm ** 2), np.full((N, 1), -0.2, F32)], axis=1)
+    w = np.exp(dist / F32(0.1 ** 2)).astype(F32)
+    S = w.sum(axis=1) + F32(1e-6)
+    out = (w * s).sum(axis=1) / S
+    l = np.abs(out)
+    kept = l < F32(clamp)
+    n_kept = int(kept.sum())
+    terms = {'surface': (l[kept].mean() if n_kept else np.float32('nan'))}
+    # ---- backward: surface term
+    g_out = np.where(kept, np.sign(out), 0).astype(F32) * F32(lambdas.get('surface', 0.0)) / F32(max(n_kept, 1))
+    if n_kept == 0:
+        g_out = g_out * np.float32('nan')
+    g_s = g_out[:, None] * w / S[:, None]
+    g_w = g_out[:, None] * (s - out[:, None]) / S[:, None]
+    g_dist = g_w * w / F32(0.1 ** 2)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        coef = np.where(r > 0, g_dist[:, :K] * F32(-2.0) * nrm / r, 0).astype(F32)
+    g_anchor = (coef[:, :, None] * diff).sum(axis=0)                       # blend path, (K,3)
+    grad = np.zeros_like(z)
+    for k in range(A):
+        ws = p.ws[k]
+        inp, pre = saved[k]
+        g = g_s[:, k:k + 1] * p.W[p.n_lin - 1][ws]                          # dL/dh3
+        g_inp = np.zeros_like(inp)
+        for layer in range(p.n_lin - 2, -1, -1):
+            h_in, a = pre[layer]
+            g_a = g * _sigmoid100(a)
+            g = g_a @ p.W[layer][ws]
+            if layer == p.skip:
+                g = g / r2
+                n_h = g.shape[1] - inp.shape[1]
+                g_inp += g[:, n_h:]
+                g = g[:, :n_h]
+        g_inp += g
+        g_c = g_inp[:, :3].sum(axis=0)
+        g_u = g_inp[:, 3:].sum(axis=0)
+        grad[:G] += g_u[:G]
+        grad[G + k * L:G + (k + 1) * L] += g_u[G:]
+        if k < K:
+            g_anchor[k] += -g_c * flip[k]                                  # c = (x - a) * flip
+    # ---- anchors -> z_glob through mlp_pos
+    g_o = g_anchor.reshape(-1).astype(F32)
+    g_h1 = (p.pos_W[2].T @ g_o) * (a1 > 0)
+    g_h0 = (p.pos_W[1].T @ g_h1) * (a0 > 0)
+    grad[:G] += p.pos_W[0].T @ g_h0
+    # ---- regularisers
+    terms['reg_global'] = float((z[:G] ** 2).sum())
+    terms['reg_loc'] = float((z[G:] ** 2).sum())
+    grad[:G] += F32(lambdas.get('reg_global', 0.0)) * 2 * z[:G]
+    grad[G:] += F32(lambdas.get('reg_loc', 0.0)) * 2 * z[G:]
+    ru = 0.0
+    for k in (30, 31, 39):
+        zk = z[G + k * L:G + (k + 1) * L]
+        ru += float((zk ** 2).sum())
+        grad[G + k * L:G + (k + 1) * L] += F32(lambdas.get('reg_unobserved', 0.0)) * 2 * zk
+    terms['reg_unobserved'] = ru
+    pairs = z[G:G + 2 * p.n_symm * L].reshape(p.n_symm, 2, L)
+    dvec = pairs[:, 0] - pairs[:, 1]
+    dn = np.sqrt((dvec ** 2).sum(axis=1))
+    terms['symm_dist'] = float(dn.mean()) if p.n_symm else 0.0
+    with np.errstate(divide='ignore', invalid='ignore'):
+        gd = np.where(dn[:, None] > 0, dvec / dn[:, None], 0) / max(p.n_symm, 1) * F32(lambdas.get('symm_dist', 0.0))
+    gpairs = np.stack([gd, -gd], axis=1).reshape(-1)
+    grad[G:G + 2 * p.n_symm * L] += gpairs.astype(F32)
+    return terms, grad.astype(F32), n_kept

@@ -145,24 +145,45 @@ def main():
 
     # ---------------------------------------------------------------- identity-space fitting trajectory
     # 3 synthetic observations of 300 points; schedule compressed with step_scale=0.01 so that 10 iterations
-    # pass every lr / lambda / clamp event of fitting_pointclouds.py:253-266.
+    # pass every lr / lambda / clamp event of fitting_pointclouds.py:253-266.  The reference code runs
+    # unmodified; torch.optim.Adam is wrapped only to RECORD the gradient / parameter it is handed each step.
+    import torch.optim as optim_mod
     rng = np.random.RandomState(100)
     obs = [(rng.randn(300, 3) * 0.12 + np.array([0.0, 0.05, -0.1])).astype(np.float32) for _ in range(3)]
+    record = {'grad': [], 'z_before': [], 'lr': []}
+    real_adam = optim_mod.Adam
+
+    class RecordingAdam(real_adam):
+        def step(self, closure=None):
+            p = self.param_groups[0]['params'][0]
+            record['grad'].append(p.grad.detach().clone().numpy().reshape(-1))
+            record['z_before'].append(p.detach().clone().numpy().reshape(-1))
+            record['lr'].append(self.param_groups[0]['lr'])
+            return super().step(closure)
+
+    optim_mod.Adam = RecordingAdam
     traj = {}
-    for n_iter in (1, 2, 3, 6, 10):
+    try:
+        n_iter = 12
         dec = make_ensemble(0, anchors)
         dec.train()                                                    # fitting_pointclouds.py:268
         lambdas = {'surface': 2.0, 'reg_global': 0.25, 'reg_unobserved': 10, 'reg_loc': 0.05, 'symm_dist': 5.0}
+        traj['lambdas_initial'] = np.array([lambdas[k] for k in sorted(lambdas)], np.float64)
         schedule = {'lr': {200: 2, 400: 2, 600: 2, 800: 2}, 'symm_dist': {200: 10, 500: 9999},
                     'reg_glob': {200: 3, 600: 10}, 'reg_loc': {500: 3, 600: 10}}
         np.random.seed(0)
         torch.manual_seed(0)                                           # fitting_pointclouds.py:230-231
         z, anc = inference_identity_space(dec, [torch.from_numpy(o) for o in obs], lambdas,
                                           n_steps=n_iter * 100, schedule_cfg=schedule, step_scale=0.01)
-        traj['z_after_%d' % n_iter] = z.detach().numpy().reshape(-1)
-        traj['anchors_after_%d' % n_iter] = anc.detach().numpy().reshape(39, 3)
-        traj['lambdas_after_%d' % n_iter] = np.array([lambdas[k] for k in sorted(lambdas)], np.float64)
-        print('fit', n_iter, 'iters: |z| =', float(z.norm()))
+    finally:
+        optim_mod.Adam = real_adam
+    traj['z_final'] = z.detach().numpy().reshape(-1)
+    traj['anchors_final'] = anc.detach().numpy().reshape(39, 3)
+    traj['lambdas_final'] = np.array([lambdas[k] for k in sorted(lambdas)], np.float64)
+    traj['grads'] = np.stack(record['grad'])
+    traj['z_before'] = np.stack(record['z_before'])
+    traj['lrs'] = np.array(record['lr'], np.float64)
+    print('fit', n_iter, 'iters: |z| =', float(z.detach().norm()), 'grad norms', np.linalg.norm(traj['grads'], axis=1)[:4])
     np.savez_compressed(os.path.join(HERE, 'fit_identity.npz'), obs=np.stack(obs), **traj)
 
 
