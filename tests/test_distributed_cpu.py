@@ -1,0 +1,98 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: slab planning, count exchange, id offsets, gather.
+The marching-cubes kernels are replaced by the oracle's sequential restatement applied per slab (ghost layer
+emulated by running the oracle on the planes up to the slab and keeping only the new part)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import noise_volume
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_plan_slabs_covers_all_layers():
+    from nphm_b200.distributed import plan_slabs, slab_planes
+    for res, world in ((256, 8), (512, 8), (20, 3), (5, 8), (2, 2)):
+        plan = plan_slabs(res, world)
+        assert plan[0][0] == 0 and plan[-1][1] == res - 1
+        assert all(a[1] == b[0] for a, b in zip(plan[:-1], plan[1:]))
+        sizes = [c1 - c0 for c0, c1 in plan]
+        assert max(sizes) - min(sizes) <= 1
+        for c0, c1 in plan:
+            p0, n, ghost = slab_planes(c0, c1)
+            if c1 > c0:
+                assert p0 == max(c0 - 1, 0) and p0 + n == c1 + 1 and ghost == (c0 > 0)
+            else:
+                assert n == 0
+
+
+def _oracle_slab_mc(vol_full):
+    """CPU stand-ins for marching_cubes_count / emit with the same slab semantics as the CUDA kernels."""
+    from oracle import nphm_oracle as O
+
+    def count(vol, iso, negate, x_global0=0, ghost_lo=False):
+        upto = x_global0 + vol.shape[0]
+        v_all, t_all = O.marching_cubes(vol_full[:upto], iso, negate)
+        first_own_layer = x_global0 + (1 if ghost_lo else 0)
+        if first_own_layer > 0:
+            v_prev, t_prev = O.marching_cubes(vol_full[:first_own_layer + 1], iso, negate)
+        else:
+            v_prev, t_prev = np.zeros((0, 3)), np.zeros((0, 3), np.uint64)
+        # sequential numbering: everything the earlier layers created comes first
+        assert np.array_equal(v_all[:len(v_prev)], v_prev) and np.array_equal(t_all[:len(t_prev)], t_prev)
+        own_v, own_t = v_all[len(v_prev):], t_all[len(t_prev):]
+        return len(own_v), len(own_t), (own_v, own_t, len(v_prev)), None
+
+    def emit(vol, params, ws, nv, nt, base):
+        own_v, own_t, n_prev = params
+        assert base == n_prev                               # id base from the count exchange == sequential numbering
+        return torch.from_numpy(own_v.copy()), torch.from_numpy(own_t.astype(np.int64))
+
+    return count, emit
+
+
+def _worker(rank, world, port, res, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from nphm_b200.distributed import exchange_counts, extract_mesh_sharded
+        from oracle import nphm_oracle as O
+        vol_full = noise_volume((res, 6, 7), seed=21)
+        counts = exchange_counts(10 + rank, 20 + rank)
+        assert counts == [(10 + r, 20 + r) for r in range(world)]
+        count, emit = _oracle_slab_mc(vol_full)
+        verts, tris = extract_mesh_sharded(lambda p0, n: torch.from_numpy(vol_full[p0:p0 + n]), res, 0.0, False,
+                                           mc_count=count, mc_emit=emit)
+        if rank == 0:
+            rv, rt = O.marching_cubes(vol_full, 0.0)
+            ok = np.array_equal(verts.numpy(), rv) and np.array_equal(tris.numpy().astype(np.uint64), rt)
+            q.put(bool(ok))
+        else:
+            assert verts is None and tris is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_extraction_two_ranks_gloo():
+    ctx = mp.get_context('spawn')
+    for world, res in ((2, 9), (2, 2)):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, res, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(180)
+            assert p.exitcode == 0
+        assert q.get() is True
