@@ -15,13 +15,13 @@
 // Activations are kept in "log2 units": t = a * 100*log2(e), sp'(t) = max(t,0) + lg2(1 + 2^-|t|) = 100*log2(e) *
 // softplus_100(a), so the softplus costs 2 MUFU + 3 ALU and the unit change is folded into biases / w4.
 //
-// Data flow per CTA (persistent, one CTA per SM, 10 warps):
-//   warp 8  : bulk-async-copy (TMA engine, cp.async.bulk) producer: streams pre-split fp16 weight slabs
+// Data flow per CTA (persistent, one CTA per SM, 18 warps):
+//   warp 16 : bulk-async-copy (TMA engine, cp.async.bulk) producer: streams pre-split fp16 weight slabs
 //             (N x 16 K-columns, hi|lo, UMMA no-swizzle K-major core-matrix order) from L2 into a 14-slot ring,
 //             and the per-(query,member) constant record (layer-0 weights, biases, w4, anchor) into a 2-slot ring.
-//   warp 9  : allocates TMEM, single-thread tcgen05.mma issuer: A (activations) from TMEM, B (weights) from smem,
+//   warp 17 : allocates TMEM, single-thread tcgen05.mma issuer: A (activations) from TMEM, B (weights) from smem,
 //             D (fp32) in TMEM; tcgen05.commit releases ring slots and signals the epilogue.
-//   warps 0-7: thread = point (TMEM lane) x column half: read D with tcgen05.ld, softplus, split to fp16 hi/lo,
+//   warps 0-15: thread = point (TMEM lane) x column group: read D with tcgen05.ld, softplus, split to fp16 hi/lo,
 //             write the next layer's A operand back to TMEM with tcgen05.st, pre-load D with the next bias.
 // TMEM map (columns): D [0,208)  A_hi [208,312)  A_lo [312,416)   (fp16 pairs, 2 K-values per column).
 #include "engine.cuh"
