@@ -26,6 +26,7 @@
 // TMEM map (columns): D [0,208)  A_hi [208,312)  A_lo [312,416)   (fp16 pairs, 2 K-values per column).
 #include "engine.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace nphm {
 namespace tc {
@@ -140,6 +141,32 @@ __device__ __forceinline__ float sp_t(float t)
     return fmaxf(t, 0.0f) + l;
 }
 
+// same, with lg2(1 + e) evaluated on the FMA pipe: e * P6(e), |error| < 4.4e-7 (log2 units) on e in [0, 1].
+// Used for every other element so that the MUFU pipe (16 lanes/clk/SM) and the issue slots are balanced.
+__device__ __forceinline__ float sp_t_poly(float t)
+{
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+    float pl = fmaf(e, 0.015529831517364317f, -0.0795574350973204f);
+    pl = fmaf(pl, e, 0.1942939234405454f);
+    pl = fmaf(pl, e, -0.3259017087892866f);
+    pl = fmaf(pl, e, 0.4735533221244069f);
+    pl = fmaf(pl, e, -0.720585455006072f);
+    pl = fmaf(pl, e, 1.4426678284772665f);
+    return fmaf(pl, e, fmaxf(t, 0.0f));
+}
+// softplus of 8 (4) accumulator values: even elements through MUFU lg2, odd ones through the polynomial
+__device__ __forceinline__ void sp8(const uint32_t (&r)[8], float (&v)[8])
+{
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) { v[e] = sp_t(__uint_as_float(r[e])); v[e + 1] = sp_t_poly(__uint_as_float(r[e + 1])); }
+}
+__device__ __forceinline__ void sp4(const uint32_t (&r)[4], float (&v)[4])
+{
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) { v[e] = sp_t(__uint_as_float(r[e])); v[e + 1] = sp_t_poly(__uint_as_float(r[e + 1])); }
+}
+
 // split two fp32 values into packed fp16 (hi, lo) pairs; element 0 in the low half (lower K index)
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
 {
@@ -181,6 +208,28 @@ __device__ __forceinline__ void store_a8(uint32_t tmem_lane_base, int k0, const 
     for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
     tc_st4(tmem_lane_base + kColAhi + (k0 >> 1), hi);
     tc_st4(tmem_lane_base + kColAlo + (k0 >> 1), lo);
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st2(uint32_t taddr, uint32_t a, uint32_t b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void store_a4(uint32_t tmem_lane_base, int k0, const float (&v)[4])
+{
+    uint32_t h0, l0, h1, l1;
+    split2(v[0], v[1], h0, l0); split2(v[2], v[3], h1, l1);
+    tc_st2(tmem_lane_base + kColAhi + (k0 >> 1), h0, h1);
+    tc_st2(tmem_lane_base + kColAlo + (k0 >> 1), l0, l1);
+}
+__device__ __forceinline__ void init_d4(uint32_t tmem_lane_base, int col, const float *bias)
+{
+    const float4 b0 = *reinterpret_cast<const float4 *>(bias + col);
+    const uint32_t r[4] = {__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w)};
+    tc_st4(tmem_lane_base + kColD + col, r);
 }
 // preload 8 accumulator columns with a bias vector from shared memory
 __device__ __forceinline__ void init_d8(uint32_t tmem_lane_base, int col, const float *bias)
@@ -280,9 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         }
     } else {
         // =========================================================================== compute / epilogue warps
-        // thread = (point row, column group): warp w serves TMEM lanes 32*(w&3).. and the 8-column chunks
-        // c = part, part+4, ...  of every layer.  A chunk is always read, re-initialised and converted by the same
-        // thread, so the only cross-warp exchange is the final dot-product reduction.
+        // thread = (point row, column group): warp w serves TMEM lanes 32*(w&3).. and column group part = w>>2.
         const int q = warp & 3, part = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
@@ -313,21 +360,37 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 if (rec[kRecMisc + 5] != 0.f) cx = -cx;          // mirrored member
                 cx *= kS; cy *= kS; cz *= kS;                   // coordinates in log2 units
 
+                // Column ownership (balanced: 6.5 chunks per warp and layer): 8-column chunks c = part + 4i (i < 6)
+                // cover columns 0..191, the 4-column piece 192 + 4*part covers 192..207; for the 112-column layer 1:
+                // chunks part + 4i (i < 3) and the piece 96 + 4*part.  A column is always read, converted and
+                // re-initialised by the same thread (stages with different ownership are separated by the quarter barrier).
+                const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
+
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1; D preloaded with S*b1
-                {
-                    const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
 #pragma unroll 1
-                    for (int c = part; c < 26; c += kParts) {
-                        const int n0 = c * 8;
-                        float v[8];
+                for (int c = part; c < 24; c += kParts) {
+                    const int n0 = c * 8;
+                    float v[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float4 w = l0[n0 + e];         // rows >= 200 are zero: sp(0) meets zero weights
-                            v[e] = sp_t(fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w))));
-                        }
-                        store_a8(tl, n0, v);
-                        if (c < 14) init_d8(tl, n0, rec + kRecB1);
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 w = l0[n0 + e];
+                        const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
+                        v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
+                    store_a8(tl, n0, v);
+                    if (c < 12) init_d8(tl, n0, rec + kRecB1);
+                }
+                {
+                    const int n0 = 192 + 4 * part;               // rows >= 200 are zero: sp(0) meets zero weights
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 w = l0[n0 + e];
+                        const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
+                        v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
+                    }
+                    store_a4(tl, n0, v);
+                    init_d4(tl, 96 + 4 * part, rec + kRecB1);
                 }
                 tc_wait_st();
                 tc_fence_before();
@@ -339,25 +402,31 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 d_ph ^= 1;
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = part; c < 26; c += kParts) {
+                for (int c = part; c < 12; c += kParts) {
                     const int n0 = c * 8;
-                    if (c < 14) {
-                        float v[8];
-                        if (c < 13) {
-                            uint32_t r[8];
-                            tc_ld8(tl + kColD + n0, r);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = sp_t(__uint_as_float(r[e]));
-                            if (c == 12) { v[5] = cx; v[6] = cy; v[7] = cz; }       // k = 101..103: local coordinates
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = 0.f;                 // k = 104..111: padding
-                        }
-                        store_a8(tl, n0, v);
-                    }
+                    uint32_t r[8];
+                    tc_ld8(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    float v[8];
+                    sp8(r, v);
+                    store_a8(tl, n0, v);
                     init_d8(tl, n0, rec + kRecB2);
                 }
+                {
+                    const int n0 = 96 + 4 * part;                // 96..99 | 100, c | padding | padding
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (part < 2) {
+                        uint32_t r[4];
+                        tc_ld4(tl + kColD + n0, r);
+                        tc_wait_ld();
+                        if (part == 0) sp4(r, v);
+                        else { v[0] = sp_t(__uint_as_float(r[0])); v[1] = cx; v[2] = cy; v[3] = cz; }
+                    }
+                    store_a4(tl, n0, v);
+                    init_d4(tl, n0, rec + kRecB2);
+                }
+#pragma unroll 1
+                for (int c = 14 + part; c < 26; c += kParts) init_d8(tl, c * 8, rec + kRecB2);   // columns 112..207
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -368,16 +437,25 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 d_ph ^= 1;
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = part; c < 26; c += kParts) {
+                for (int c = part; c < 24; c += kParts) {
                     const int n0 = c * 8;
                     uint32_t r[8];
                     tc_ld8(tl + kColD + n0, r);
                     tc_wait_ld();
                     float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = sp_t(__uint_as_float(r[e]));
+                    sp8(r, v);
                     store_a8(tl, n0, v);
                     init_d8(tl, n0, rec + kRecB3);
+                }
+                {
+                    const int n0 = 192 + 4 * part;
+                    uint32_t r[4];
+                    tc_ld4(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    float v[4];
+                    sp4(r, v);
+                    store_a4(tl, n0, v);
+                    init_d4(tl, n0, rec + kRecB3);
                 }
                 tc_wait_st();
                 tc_fence_before();
@@ -390,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 tc_fence_after();
                 float acc = 0.f;
 #pragma unroll 1
-                for (int c = part; c < 26; c += kParts) {
+                for (int c = part; c < 24; c += kParts) {
                     const int n0 = c * 8;
                     uint32_t r[8];
                     tc_ld8(tl + kColD + n0, r);
@@ -398,8 +476,22 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     const float4 w0 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0);
                     const float4 w1 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0 + 4);
                     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float v[8];
+                    sp8(r, v);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc = fmaf(sp_t(__uint_as_float(r[e])), w[e], acc);   // w4 pad = 0
+                    for (int e = 0; e < 8; ++e) acc = fmaf(v[e], w[e], acc);                  // w4 pad = 0
+                }
+                {
+                    const int n0 = 192 + 4 * part;
+                    uint32_t r[4];
+                    tc_ld4(tl + kColD + n0, r);
+                    tc_wait_ld();
+                    const float4 w0 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0);
+                    const float w[4] = {w0.x, w0.y, w0.z, w0.w};
+                    float v[4];
+                    sp4(r, v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc = fmaf(v[e], w[e], acc);
                 }
                 if (part != 0) sm.partial[part - 1][row] = acc;
                 tc_fence_before();
@@ -671,5 +763,59 @@ extern "C" int nphm_debug_tc_mma(const float *a_dev, const float *b_dev, int n, 
     cudaError_t e = cudaStreamSynchronize(stream);
     cudaFree(slabs);
     if (e != cudaSuccess) { set_error("nphm_debug_tc_mma: %s", cudaGetErrorString(e)); return NPHM_ERR_CUDA; }
+    return NPHM_OK;
+}
+
+// Micro-benchmark: `iters` MMAs (M=128, K=16, A from TMEM, B from smem) accumulating into one D (alternate=0) or
+// round-robin into `alternate` disjoint D ranges; returns SM cycles from first issue to commit completion.
+namespace nphm { namespace tc {
+__global__ void __launch_bounds__(160, 1) mma_bench_kernel(int n, int iters, int alternate, long long *cycles)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 208 * 64 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (threadIdx.x == 128) {
+        const uint32_t idesc = make_idesc(n);
+        const uint64_t b = make_desc(smem_u32(smem_raw), 128, 256);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const int d = alternate > 1 ? (i % alternate) * n : 0;
+            tc_mma_ts(tmem + d, tmem + 448, b, idesc, 1);
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        cycles[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+}}
+extern "C" int nphm_debug_tc_mma_bench(int n, int iters, int alternate, long long *cycles_host)
+{
+    using namespace nphm;
+    long long *d = nullptr;
+    NPHM_CUDA_CHECK(cudaMalloc(&d, 8));
+    const int smem = 208 * 64 + 1024;
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::mma_bench_kernel<<<1, 160, smem>>>(n, iters, alternate, d);
+    cudaError_t e = cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("nphm_debug_tc_mma_bench: %s", cudaGetErrorString(e)); return NPHM_ERR_CUDA; }
     return NPHM_OK;
 }
