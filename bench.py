@@ -209,12 +209,15 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
         flush.zero_()
+    import gc
+    gc.collect()
+    gc.disable()                        # no collector pauses inside the timed regions (host sits between MC passes)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     launches['n'] = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     ev[0].record()
     n_tris = 0
     for i in range(args.steps):
@@ -222,18 +225,24 @@ def main():
         eng.query_grid(lat, MINI, MAXI, res, 0, total, quirk_period=CHUNK, out=volume)
         kev[i][1].record()
         v, t = _native.marching_cubes_device(volume.view(res, res, res), 0.0, negate=True)
+        kev[i][2].record()
         launches['n'] += 8
         n_tris = t.shape[0]
-        flush.zero_()                   # L2 flush between timed iterations (inside the timed region, ~0.1 ms)
+        flush.zero_()                   # L2 flush between timed iterations (inside the timed region)
+        kev[i][3].record()
     ev[1].record()
     barrier()
     clocks = sampler.stop()
     ms_total = ev[0].elapsed_time(ev[1])
-    sdf_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))   # prep kernels + the ensemble kernel
-    t = torch.tensor([ms_total, sdf_ms], device=dev, dtype=torch.float64)
+    if os.environ.get('NPHM_BENCH_DEBUG'):
+        print('per-step ms (sdf, mc, flush):', [[round(k[j].elapsed_time(k[j + 1]), 3) for j in range(3)] for k in kev], file=sys.stderr)
+    sdf_ms = float(np.mean([k[0].elapsed_time(k[1]) for k in kev]))   # prep kernels + the ensemble kernel
+    mc_ms = float(np.mean([k[1].elapsed_time(k[2]) for k in kev]))    # marching cubes (4 kernels + count readback)
+    flush_ms = float(np.mean([k[2].elapsed_time(k[3]) for k in kev]))
+    t = torch.tensor([ms_total, sdf_ms, mc_ms, flush_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, sdf_ms = t.tolist()
+    ms_total, sdf_ms, mc_ms, flush_ms = t.tolist()
     ms_per_step = ms_total / args.steps
     value = world * total / (ms_per_step * 1e-3)
 
@@ -264,6 +273,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * total / e2e_s.item()
+    gc.enable()
 
     if rank == 0:
         peaks = {}
@@ -285,7 +295,7 @@ def main():
                        'res': res, 'nbatch_points': CHUNK, 'impl': args.impl, 'l2': 'flushed between iterations (256 MB write)',
                        'triangles': int(n_tris)},
             'meshes_per_s': world / (ms_per_step * 1e-3),
-            'sdf_ms': sdf_ms, 'mc_ms': ms_per_step - sdf_ms,
+            'sdf_ms': sdf_ms, 'mc_ms': mc_ms, 'l2_flush_ms': flush_ms,
             'gpu_launches': launches['n'],
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),

@@ -38,7 +38,7 @@ constexpr int kNP1 = 112, kNP2 = 208, kNP3 = 208;
 constexpr int kKS1 = 13, kKS2 = 7, kKS3 = 13;       // k-steps of 16
 constexpr int kSlab1Bytes = kNP1 * 64;               // hi + lo, 16 K-columns
 constexpr int kSlabBytes = kNP2 * 64;
-constexpr int kSlots = 14;
+constexpr int kGroupBytes = 7 * kSlabBytes;             // weight groups: L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
 constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3Bytes = kKS3 * kSlabBytes;
 constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
 constexpr int kColD = 0, kColAhi = 208, kColAlo = 312, kTmemCols = 512;
@@ -178,10 +178,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
 }
 
 struct __align__(128) Smem {
-    uint8_t slabs[kSlots][kSlabBytes];
+    uint8_t wbuf[2][kGroupBytes];            // double-buffered weight groups (one bulk copy + one barrier each)
     float rec[2][kRecFloats];
     float partial[kParts - 1][128];
-    uint64_t slab_full[kSlots], slab_empty[kSlots];
+    uint64_t w_full[2], w_empty[2];
     uint64_t rec_full[2], rec_empty[2];
     uint64_t a_ready, d_ready;
     uint32_t tmem_base;
@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     const long long n_tiles = tiles_per_query * p.n_queries;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&sm.slab_full[i], 1); mbar_init(&sm.slab_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1);
+            mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps);
+        }
         mbar_init(&sm.a_ready, kEpiWarps);
         mbar_init(&sm.d_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -269,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     if (warp == kEpiWarps) {
         // =========================================================================== producer (bulk async copies)
         if (lane == 0) {
-            int slot = 0, rslot = 0;
-            uint32_t ph = 0, rph = 0;
+            int wb = 0, rslot = 0;
+            uint32_t wph = 0, rph = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int qi = (int)(tile / tiles_per_query);
                 for (int m = 0; m < p.n_members; ++m) {
@@ -282,13 +284,13 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     const int set = m < 2 * p.n_symm ? (m >> 1) : m - p.n_symm;
                     const uint8_t *w = p.weights + (size_t)set * kSetBytes;
 #pragma unroll 1
-                    for (int j = 0; j < kKS1 + kKS2 + kKS3; ++j) {
-                        const uint32_t bytes = j < kKS1 ? kSlab1Bytes : kSlabBytes;
-                        mbar_wait(&sm.slab_empty[slot], ph ^ 1);
-                        mbar_expect_tx(&sm.slab_full[slot], bytes);
-                        bulk_g2s(sm.slabs[slot], w, bytes, &sm.slab_full[slot]);
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t bytes = g == 0 ? kL1Bytes : (g == 1 ? kL2Bytes : (g == 2 ? 7 * kSlabBytes : 6 * kSlabBytes));
+                        mbar_wait(&sm.w_empty[wb], wph ^ 1);
+                        mbar_expect_tx(&sm.w_full[wb], bytes);
+                        bulk_g2s(sm.wbuf[wb], w, bytes, &sm.w_full[wb]);
                         w += bytes;
-                        if (++slot == kSlots) { slot = 0; ph ^= 1; }
+                        if (++wb == 2) { wb = 0; wph ^= 1; }
                     }
                 }
             }
@@ -296,33 +298,37 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     } else if (warp == kEpiWarps + 1) {
         // =========================================================================== MMA issuer
         if (lane == 0) {
-            int slot = 0;
-            uint32_t ph = 0, a_ph = 0;
+            int wb = 0;
+            uint32_t wph = 0, a_ph = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int m = 0; m < p.n_members; ++m) {
 #pragma unroll 1
-                    for (int layer = 0; layer < 3; ++layer) {
-                        const int ks = layer == 0 ? kKS1 : (layer == 1 ? kKS2 : kKS3);
-                        const int n = layer == 0 ? kNP1 : kNP2;
+                    for (int g = 0; g < 4; ++g) {
+                        // group -> (layer shape, k-step range): L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
+                        const int n = g == 0 ? kNP1 : kNP2;
+                        const int ks = g == 0 ? kKS1 : (g == 3 ? 6 : 7);
+                        const int k0 = g == 3 ? 7 : 0;
                         const uint32_t idesc = make_idesc(n);
-                        mbar_wait(&sm.a_ready, a_ph);
-                        a_ph ^= 1;
+                        if (g != 3) {
+                            mbar_wait(&sm.a_ready, a_ph);
+                            a_ph ^= 1;
+                        }
+                        mbar_wait(&sm.w_full[wb], wph);
                         tc_fence_after();
+                        const uint32_t base = smem_u32(sm.wbuf[wb]);
 #pragma unroll 1
                         for (int j = 0; j < ks; ++j) {
-                            mbar_wait(&sm.slab_full[slot], ph);
-                            tc_fence_after();
-                            const uint32_t base = smem_u32(sm.slabs[slot]);
-                            const uint64_t b_hi = make_desc(base, 128, 256);
-                            const uint64_t b_lo = make_desc(base + n * 32, 128, 256);
-                            const uint32_t a_hi = tmem + kColAhi + j * 8, a_lo = tmem + kColAlo + j * 8;
+                            const uint32_t slab = base + j * n * 64;
+                            const uint64_t b_hi = make_desc(slab, 128, 256);
+                            const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
+                            const uint32_t a_hi = tmem + kColAhi + (k0 + j) * 8, a_lo = tmem + kColAlo + (k0 + j) * 8;
                             tc_mma_ts(tmem + kColD, a_hi, b_hi, idesc, 1);
                             tc_mma_ts(tmem + kColD, a_hi, b_lo, idesc, 1);
                             tc_mma_ts(tmem + kColD, a_lo, b_hi, idesc, 1);
-                            tc_commit(&sm.slab_empty[slot]);
-                            if (++slot == kSlots) { slot = 0; ph ^= 1; }
                         }
-                        tc_commit(&sm.d_ready);
+                        tc_commit(&sm.w_empty[wb]);
+                        if (g != 2) tc_commit(&sm.d_ready);
+                        if (++wb == 2) { wb = 0; wph ^= 1; }
                     }
                 }
             }

@@ -16,6 +16,7 @@ import torch
 
 from .EnsembledDeepSDF import FastEnsembleDeepSDFMirrored
 from ..utils.mesh import make_mesh
+from ..utils.reconstruction import _to_host
 
 
 def _as_row(encoding: torch.Tensor) -> torch.Tensor:
@@ -32,7 +33,7 @@ def get_logits(decoder, encoding, grid_points, nbatch_points=100000, return_anch
             period = 0 if decoder.training else int(nbatch_points)
             sdf, anchors = decoder.engine().query(pts, _as_row(encoding).to(pts.device), eval_quirk=not decoder.training,
                                                   quirk_period=period if period else None)
-            logits = sdf.reshape(-1).cpu().numpy()
+            logits = _to_host(sdf.reshape(-1))
         else:
             outs = []
             anchors = None

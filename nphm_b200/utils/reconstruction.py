@@ -29,11 +29,29 @@ def create_grid_points_from_bounds(minimun, maximum, res, scale=None):
 
 def marching_cubes(volume, isovalue=0.0):
     """== ``mcubes.marching_cubes(volume, isovalue)`` on the GPU: (verts (V,3) float64 in index units,
-    tris (T,3) uint64).  Accepts a numpy array (host round trip) or a CUDA tensor."""
+    tris (T,3) uint64).  Accepts a numpy array (host round trip through torch's pinned staging and caching
+    allocator) or a CUDA tensor."""
     if isinstance(volume, torch.Tensor) and volume.is_cuda:
         v, t = _native.marching_cubes_device(volume.float(), isovalue)
         return v.cpu().numpy(), t.cpu().numpy().view(np.uint64)
-    return _native.marching_cubes_host(np.asarray(volume), isovalue)
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    if vol.ndim != 3:
+        raise ValueError('marching_cubes expects a 3-D volume')
+    if torch.cuda.is_available():
+        dev = torch.device('cuda', torch.cuda.current_device())
+        v, t = _native.marching_cubes_device(torch.from_numpy(vol).to(dev), isovalue)
+        return _to_host(v), _to_host(t).view(np.uint64)
+    return _native.marching_cubes_host(vol, isovalue)          # raises: there is no CPU fallback
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy through a pinned buffer of torch's caching host allocator."""
+    if t.numel() == 0:
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out.numpy()
 
 
 def mesh_from_logits(logits, mini, maxi, resolution):
