@@ -246,6 +246,27 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * total / (ms_per_step * 1e-3)
 
+    # ---- opt-in pruned kernel (reported separately; NOT the dense reference computation) ---------------------
+    pruned = None
+    if world == 1 and args.impl in ('auto', 'tc'):
+        tau = 1e-8
+        eng.set_prune_threshold(tau)
+        ref_vol = volume.clone()
+        pv = torch.empty_like(volume)
+        for _ in range(2):
+            eng.query_grid(lat, MINI, MAXI, res, 0, total, quirk_period=CHUNK, out=pv, impl='tc_pruned')
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            eng.query_grid(lat, MINI, MAXI, res, 0, total, quirk_period=CHUNK, out=pv, impl='tc_pruned')
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / args.steps
+        pruned = {'tau': tau, 'sdf_ms': pms, 'value': total / (pms * 1e-3), 'unit': 'points/s',
+                  'max_abs_diff_vs_dense': float((pv - ref_vol).abs().max().item()),
+                  'note': 'NPHM_IMPL_TC_PRUNED: members with normalised blend weight < tau on a whole 8x4x4 tile are skipped'}
+
     # ---- end to end through the drop-in API with host buffers ---------------------------------------------
     grid_points = torch.from_numpy(create_grid_points_from_bounds(MINI, MAXI, res)).to(dev, dtype=torch.float)
     grid_points = grid_points.reshape(1, -1, 3)                 # uploaded once, like fitting_pointclouds.py:166-170
@@ -305,6 +326,8 @@ def main():
                          'note': 'dominant kernel = fused ensemble SDF query; algorithmic 9.616 MFLOP/point (dense '
                                  'reference formulation) / CUDA-event time of the query; peak: ' + peak_src},
         }
+        if pruned is not None:
+            line['pruned_opt_in'] = pruned
         if not args.no_cpu_baseline and world == 1:
             v, detail = cpu_reference_sample(res, args.cpu_sample_chunks)
             line['cpu_baseline'] = {'value': v, 'unit': 'points/s', 'cores': os.cpu_count() or 1, 'kind': 'port',

@@ -30,6 +30,9 @@ extern "C" {
 #define NPHM_IMPL_AUTO   0   /* tcgen05 kernel when the configuration allows it, else SIMT */
 #define NPHM_IMPL_SIMT   1   /* fp32 FFMA kernel (any configuration) */
 #define NPHM_IMPL_TC     2   /* tcgen05 / TMEM kernel, 3-pass fp16 split (fp32-equivalent accuracy) */
+#define NPHM_IMPL_TC_PRUNED 3 /* OPT-IN: tcgen05 kernel that skips, per compact tile of 128 points, the ensemble members whose
+                                normalised Gaussian blend weight is < tau for every point of the tile.  Not the dense
+                                reference computation: |error| <= n_members * tau * max_k |s_k| (tau default 1e-8). */
 
 const char *nphm_last_error(void);
 int nphm_abi_version(void);
@@ -53,6 +56,8 @@ typedef struct {
 
 int nphm_ensemble_create(const nphm_ensemble_config *cfg, nphm_ensemble **out);
 void nphm_ensemble_destroy(nphm_ensemble *h);
+/* threshold tau of NPHM_IMPL_TC_PRUNED (relative blend weight below which a member is skipped), 0 <= tau < 1 */
+int nphm_ensemble_set_prune_threshold(nphm_ensemble *h, float tau);
 
 /* Replaces `load_state_dict` for the engine.  lin_w_dev[l]: (n_sets, out_l, in_l) row-major, lin_b_dev[l]:
  * (n_sets, out_l) for l = 0..n_layers (keys ensembled_deep_sdf.lin{l}.weight/bias, n_sets = n_loc+1-n_symm_pairs);

@@ -15,8 +15,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
-_IMPL_BY_NAME = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC}
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_PRUNED = 0, 1, 2, 3
+_IMPL_BY_NAME = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC, 'tc_pruned': IMPL_TC_PRUNED}
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libnphm_b200.so')
 _lib = None
@@ -24,7 +24,7 @@ _lib = None
 # every symbol include/nphm_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
     'nphm_last_error', 'nphm_abi_version', 'nphm_device_info',
-    'nphm_ensemble_create', 'nphm_ensemble_destroy', 'nphm_ensemble_load_weights',
+    'nphm_ensemble_create', 'nphm_ensemble_destroy', 'nphm_ensemble_set_prune_threshold', 'nphm_ensemble_load_weights',
     'nphm_ensemble_query', 'nphm_ensemble_query_grid', 'nphm_ensemble_get_logits_host',
     'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
     L.nphm_ensemble_create.argtypes = [POINTER(EnsembleConfig), POINTER(c_void_p)]
     L.nphm_ensemble_destroy.argtypes = [c_void_p]
     L.nphm_ensemble_destroy.restype = None
+    L.nphm_ensemble_set_prune_threshold.argtypes = [c_void_p, c_float]
     L.nphm_ensemble_load_weights.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                              POINTER(c_void_p), c_void_p, c_void_p]
     L.nphm_ensemble_query.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p,
@@ -188,6 +189,10 @@ class EnsembleEngine(_Versioned):
     @property
     def handle(self):
         return self._h
+
+    def set_prune_threshold(self, tau: float):
+        """tau of the opt-in pruned kernel (impl='tc_pruned')."""
+        check(lib().nphm_ensemble_set_prune_threshold(self._h, float(tau)), 'nphm_ensemble_set_prune_threshold')
 
     def _params(self, module):
         e = module.ensembled_deep_sdf

@@ -145,6 +145,13 @@ extern "C" int nphm_ensemble_create(const nphm_ensemble_config *cfg, nphm_ensemb
 
 extern "C" void nphm_ensemble_destroy(nphm_ensemble *h) { delete h; }
 
+extern "C" int nphm_ensemble_set_prune_threshold(nphm_ensemble *h, float tau)
+{
+    NPHM_REQUIRE(h && tau >= 0.f && tau < 1.f, "nphm_ensemble_set_prune_threshold: tau must be in [0, 1)");
+    h->tc_prune_tau = tau;
+    return NPHM_OK;
+}
+
 extern "C" int nphm_ensemble_load_weights(nphm_ensemble *h, const float *const *lin_w, const float *const *lin_b,
                                           const float *const *pos_w, const float *const *pos_b,
                                           const float *mean_anchors, void *stream_)
@@ -189,8 +196,11 @@ int ensemble_prepare(nphm_ensemble *h, const float *latents_dev, int n_queries, 
 
 static int pick_impl(nphm_ensemble *h, int impl, bool *use_tc)
 {
-    NPHM_REQUIRE(impl == NPHM_IMPL_AUTO || impl == NPHM_IMPL_SIMT || impl == NPHM_IMPL_TC, "unknown impl %d", impl);
+    NPHM_REQUIRE(impl == NPHM_IMPL_AUTO || impl == NPHM_IMPL_SIMT || impl == NPHM_IMPL_TC || impl == NPHM_IMPL_TC_PRUNED,
+                 "unknown impl %d", impl);
     const bool tc_ok = tc_ensemble_supported(h);
+    h->tc_prune = impl == NPHM_IMPL_TC_PRUNED;
+    if (impl == NPHM_IMPL_TC_PRUNED) impl = NPHM_IMPL_TC;
     if (impl == NPHM_IMPL_TC && !tc_ok) {
         set_error("tcgen05 ensemble kernel does not support this configuration");
         return NPHM_ERR_UNSUPPORTED;

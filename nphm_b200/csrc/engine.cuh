@@ -49,6 +49,8 @@ struct nphm_ensemble {
     // tensor-core path (tc_ensemble.cu)
     nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
     bool tc_ready = false;
+    bool tc_prune = false;          // opt-in member pruning (NPHM_IMPL_TC_PRUNED)
+    float tc_prune_tau = 1e-8f;
     // fitting (fit.cu)
     nphm::DeviceBuffer fit_scratch;
 };

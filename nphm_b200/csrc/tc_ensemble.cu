@@ -183,7 +183,8 @@ struct __align__(128) Smem {
     float partial[kParts - 1][128];
     uint64_t w_full[2], w_empty[2];
     uint64_t rec_full[2], rec_empty[2];
-    uint64_t a_ready, d_ready;
+    uint64_t a_ready, d_ready, mask_ready;
+    unsigned long long maskq[2][4];
     uint32_t tmem_base;
 };
 
@@ -198,6 +199,11 @@ struct Params {
     long long quirk_period;
     float *out;
     int n_members, n_symm;
+    // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
+    const float *anchors;       // [n_queries][n_members-1][3]
+    float prune_tau;
+    long long n_tiles;          // tiles to process (grid mode + pruning uses compact 8x4x4 blocks)
+    int blocked, px0, px1, by, bz;
 };
 
 // store 8 consecutive activations (next-layer K indices k0..k0+7) as fp16 hi/lo pairs
@@ -241,13 +247,14 @@ __device__ __forceinline__ void init_d8(uint32_t tmem_lane_base, int col, const 
     tc_st8(tmem_lane_base + kColD + col, r);
 }
 
+template <bool PRUNE>
 __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tiles_per_query = (p.n_points + 127) / 128;
-    const long long n_tiles = tiles_per_query * p.n_queries;
+    const long long tiles_per_query = p.blocked ? p.n_tiles : (p.n_points + 127) / 128;
+    const long long n_tiles = p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         }
         mbar_init(&sm.a_ready, kEpiWarps);
         mbar_init(&sm.d_ready, 1);
+        mbar_init(&sm.mask_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
@@ -272,10 +280,17 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         // =========================================================================== producer (bulk async copies)
         if (lane == 0) {
             int wb = 0, rslot = 0;
-            uint32_t wph = 0, rph = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t wph = 0, rph = 0, tcount = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 const int qi = (int)(tile / tiles_per_query);
+                unsigned long long mask = ~0ull;
+                if (PRUNE) {
+                    mbar_wait(&sm.mask_ready, tcount & 1);
+                    const unsigned long long *mq = sm.maskq[tcount & 1];
+                    mask = mq[0] | mq[1] | mq[2] | mq[3];
+                }
                 for (int m = 0; m < p.n_members; ++m) {
+                    if (PRUNE && !((mask >> m) & 1)) continue;
                     mbar_wait(&sm.rec_empty[rslot], rph ^ 1);
                     mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
                     bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
@@ -299,9 +314,16 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         // =========================================================================== MMA issuer
         if (lane == 0) {
             int wb = 0;
-            uint32_t wph = 0, a_ph = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t wph = 0, a_ph = 0, tcount = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                unsigned long long mask = ~0ull;
+                if (PRUNE) {
+                    mbar_wait(&sm.mask_ready, tcount & 1);
+                    const unsigned long long *mq = sm.maskq[tcount & 1];
+                    mask = mq[0] | mq[1] | mq[2] | mq[3];
+                }
                 for (int m = 0; m < p.n_members; ++m) {
+                    if (PRUNE && !((mask >> m) & 1)) continue;
 #pragma unroll 1
                     for (int g = 0; g < 4; ++g) {
                         // group -> (layer shape, k-step range): L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
@@ -340,25 +362,82 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
         int rslot = 0;
-        uint32_t rph = 0, d_ph = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int qi = (int)(tile / tiles_per_query);
-            const long long idx = (tile - (long long)qi * tiles_per_query) * 128 + row;
-            const bool valid = idx < p.n_points;
-            const long long g = p.first + (valid ? idx : 0);
+        uint32_t rph = 0, d_ph = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            int qi;
+            long long idx, g;
+            bool valid;
             float x, y, z;
-            if (p.xyz) {
-                const float *pp = p.xyz + ((size_t)qi * p.n_points + (valid ? idx : 0)) * 3;
-                x = pp[0]; y = pp[1]; z = pp[2];
+            if (p.blocked) {
+                // compact 8 x 4 x 4 block of grid points (z fastest inside the block)
+                qi = 0;
+                const long long tz = tile % p.bz, txy = tile / p.bz;
+                const int ty = (int)(txy % p.by), tx = (int)(txy / p.by);
+                const int ix = p.px0 + tx * 8 + (row >> 4), iy = ty * 4 + ((row >> 2) & 3), iz = (int)tz * 4 + (row & 3);
+                g = ((long long)ix * p.res + iy) * p.res + iz;
+                valid = ix <= p.px1 && iy < p.res && iz < p.res && g >= p.first && g < p.first + p.n_points;
+                idx = g - p.first;
+                const int cx_ = min(ix, p.res - 1), cy_ = min(iy, p.res - 1), cz_ = min(iz, p.res - 1);
+                x = __ldg(p.axes + cx_); y = __ldg(p.axes + p.res + cy_); z = __ldg(p.axes + 2 * p.res + cz_);
+                if (!valid) g = p.first;
             } else {
-                const long long rr = (long long)p.res * p.res;
-                const int ix = (int)(g / rr), iy = (int)((g - ix * rr) / p.res), iz = (int)(g % p.res);
-                x = __ldg(p.axes + ix); y = __ldg(p.axes + p.res + iy); z = __ldg(p.axes + 2 * p.res + iz);
+                qi = (int)(tile / tiles_per_query);
+                idx = (tile - (long long)qi * tiles_per_query) * 128 + row;
+                valid = idx < p.n_points;
+                g = p.first + (valid ? idx : 0);
+                if (p.xyz) {
+                    const float *pp = p.xyz + ((size_t)qi * p.n_points + (valid ? idx : 0)) * 3;
+                    x = pp[0]; y = pp[1]; z = pp[2];
+                } else {
+                    const long long rr = (long long)p.res * p.res;
+                    const int ix = (int)(g / rr), iy = (int)((g - ix * rr) / p.res), iz = (int)(g % p.res);
+                    x = __ldg(p.axes + ix); y = __ldg(p.axes + p.res + iy); z = __ldg(p.axes + 2 * p.res + iz);
+                }
             }
             const bool quirk = p.quirk_period > 0 && ((g % p.quirk_period) == p.quirk_period - 1 || g == p.total - 1);
             float num = 0.f, den = 0.f;
+            unsigned long long mask = ~0ull;
+            if (PRUNE) {
+                // blend weights of all members for this thread's point: S = sum_k w_k; a member is needed by the tile if
+                // w_k >= tau * (S + 1e-6) for at least one of its points (dropped mass per point < n_members * tau).
+                if (part == 0) {
+                    const float *anc = p.anchors + (size_t)qi * (p.n_members - 1) * 3;
+                    float S = 0.f;
+                    for (int k = 0; k < p.n_members; ++k) {
+                        float d = -0.2f;
+                        if (k < p.n_members - 1) {
+                            const float dx = __ldg(anc + 3 * k) - x, dy = __ldg(anc + 3 * k + 1) - y, dz = __ldg(anc + 3 * k + 2) - z;
+                            const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                            d = -(nrm * nrm);
+                        }
+                        S += expf(__fdiv_rn(d, 0.01f));
+                    }
+                    den = S;
+                    const float thr = p.prune_tau * (S + 1e-6f);
+                    unsigned long long wm = 0;
+                    for (int k = 0; k < p.n_members; ++k) {
+                        float d = -0.2f;
+                        if (k < p.n_members - 1) {
+                            const float dx = __ldg(anc + 3 * k) - x, dy = __ldg(anc + 3 * k + 1) - y, dz = __ldg(anc + 3 * k + 2) - z;
+                            const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                            d = -(nrm * nrm);
+                        }
+                        const bool need = valid && expf(__fdiv_rn(d, 0.01f)) >= thr;
+                        if (__any_sync(0xffffffffu, need)) wm |= 1ull << k;
+                    }
+                    wm |= 1ull << (p.n_members - 1);      // every tile evaluates >= 1 member: keeps all warps in lock step
+                    if (lane == 0) {
+                        sm.maskq[tcount & 1][q] = wm;
+                        mbar_arrive(&sm.mask_ready);
+                    }
+                }
+                mbar_wait(&sm.mask_ready, tcount & 1);
+                const unsigned long long *mq = sm.maskq[tcount & 1];
+                mask = mq[0] | mq[1] | mq[2] | mq[3];
+            }
 
             for (int m = 0; m < p.n_members; ++m) {
+                if (PRUNE && !((mask >> m) & 1)) continue;
                 mbar_wait(&sm.rec_full[rslot], rph);
                 const float *rec = sm.rec[rslot];
                 const float ax = rec[kRecMisc + 1], ay = rec[kRecMisc + 2], az = rec[kRecMisc + 3];
@@ -517,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     }
                     const float w = expf(__fdiv_rn(d, 0.01f));
                     num = fmaf(w, quirk ? 1.0f : s, num);
-                    den += w;
+                    if (!PRUNE) den += w;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.rec_empty[rslot]);
@@ -742,11 +821,25 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.xyz = q.xyz; p.axes = q.axes; p.res = q.res; p.first = q.first; p.total = q.total; p.n_points = q.n_points;
     p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out;
     p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
-    const long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;
+    const bool prune = h->tc_prune;
+    p.anchors = q.anchors; p.prune_tau = h->tc_prune_tau;
+    p.blocked = 0; p.px0 = p.px1 = 0; p.by = p.bz = 1;
+    long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;
+    if (prune && !q.xyz && q.n_points > 0) {
+        // compact blocks over the x-plane range that contains [first, first + n_points)
+        const long long rr = (long long)q.res * q.res;
+        p.px0 = (int)(q.first / rr);
+        p.px1 = (int)((q.first + q.n_points - 1) / rr);
+        p.by = (q.res + 3) / 4; p.bz = (q.res + 3) / 4;
+        n_tiles = (long long)((p.px1 - p.px0 + 8) / 8) * p.by * p.bz;
+        p.blocked = 1;
+    }
+    p.n_tiles = n_tiles;
     const int grid_x = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     const int smem = (int)sizeof(tc::Smem);
-    NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::ensemble_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    tc::ensemble_tc_kernel<<<grid_x, tc::kThreads, smem, stream>>>(p);
+    auto kern = prune ? tc::ensemble_tc_kernel<true> : tc::ensemble_tc_kernel<false>;
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid_x, tc::kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }

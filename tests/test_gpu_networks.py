@@ -182,3 +182,25 @@ def test_tensor_core_operand_plumbing(cuda_device):
             errs[variant] = float(np.abs(d.cpu().numpy() - ref).max())
         print('tc operand self-test n=%d ks=%d: max abs err by layout variant %s' % (n, ks, errs))
         assert errs[0] < 2e-5 * max(1.0, np.abs(ref).max()), errs
+
+
+def test_pruned_kernel_is_opt_in_and_within_its_error_bound(cuda_device):
+    """NPHM_IMPL_TC_PRUNED skips members with negligible blend weight: not bit-identical to the dense kernel, but
+    within n_members * tau * max|s_k| of it (and of the reference)."""
+    g = load_golden('ensemble.npz')
+    for tag, seed, scale in (('a', 0, 1.0), ('b', 5, 2.0)):
+        dec = make_ensemble(seed, scale, device=cuda_device).eval()
+        lat = torch.from_numpy(g['latent_' + tag]).to(cuda_device)
+        eng = dec.engine()
+        for res, first, count in ((40, 0, 40 ** 3), (33, 33 * 33 * 5 + 7, 33 * 33 * 9 + 100)):
+            dense, _ = eng.query_grid(lat, MINI, MAXI, res, first, count, quirk_period=2500, impl='tc')
+            for tau in (1e-8, 1e-6):
+                eng.set_prune_threshold(tau)
+                pruned, _ = eng.query_grid(lat, MINI, MAXI, res, first, count, quirk_period=2500, impl='tc_pruned')
+                err = (dense - pruned).abs().max().item()
+                print('pruned %s res %d tau %g: max abs diff vs dense %.3g' % (tag, res, tau, err))
+                assert err < 40 * tau * 1.0 + 2e-7
+        eng.set_prune_threshold(1e-8)
+        x = torch.from_numpy(g['points_' + tag]).to(cuda_device).unsqueeze(0)
+        s, _ = eng.query(x, lat.reshape(1, -1), eval_quirk=True, impl='tc_pruned')       # explicit points (no blocks)
+        assert np.abs(s.cpu().numpy().reshape(-1) - g['sdf_eval_' + tag]).max() < TOL
