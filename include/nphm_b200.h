@@ -113,7 +113,9 @@ int nphm_mlp_create(const nphm_mlp_config *cfg, nphm_mlp **out);
 void nphm_mlp_destroy(nphm_mlp *h);
 /* w_dev[l]: (out_l, in_l) row-major, b_dev[l]: (out_l), l = 0..n_layers (keys lin{l}.weight/bias). */
 int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, const float *const *b_dev, void *stream);
-/* xyz_dev n_queries*n_points*3, cond_dev n_queries*lat_dim -> out_dev n_queries*n_points*out_dim */
+/* xyz_dev n_queries*n_points*3, cond_dev n_queries*lat_dim -> out_dev n_queries*n_points*out_dim.
+ * impl: NPHM_IMPL_AUTO picks the tcgen05 kernel for the deformation-backbone configuration (hidden 512, 6 hidden layers,
+ * condition 232, 3 outputs) and the fp32 FFMA kernel otherwise; NPHM_IMPL_SIMT / NPHM_IMPL_TC force one. */
 int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries,
                    long long n_points, float *out_dev, int impl, void *stream);
 

@@ -264,6 +264,11 @@ class EnsembleEngine(_Versioned):
         return out, anchors
 
 
+def _mlp_impl(impl) -> int:
+    code = default_impl() if impl is None else impl_code(impl)
+    return IMPL_AUTO if code == IMPL_TC_PRUNED else code
+
+
 class MlpEngine(_Versioned):
     """Native handle for one ``DeepSDF`` stack (also the backbone of ``DeformationNetwork``)."""
 
@@ -309,7 +314,7 @@ class MlpEngine(_Versioned):
         out = torch.empty(B, N, self.out_dim, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             check(lib().nphm_mlp_query(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(),
-                                       IMPL_AUTO if impl is None else impl_code(impl), _stream_ptr(dev)),
+                                       _mlp_impl(impl), _stream_ptr(dev)),
                   'nphm_mlp_query')
         return out
 

@@ -305,6 +305,8 @@ extern "C" int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, con
     int rc = h->weights.load(h->dims, 1, w_dev, b_dev, static_cast<cudaStream_t>(stream_));
     if (rc) return rc;
     fill_descriptors(h->dims, h->weights, 1, 0, h->cfg.lat_dim, 0, 0, h->net, h->spec);
+    rc = tc_mlp_pack(h, static_cast<cudaStream_t>(stream_));
+    if (rc) return rc;
     h->loaded = true;
     return NPHM_OK;
 }
@@ -316,7 +318,13 @@ extern "C" int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *co
     NPHM_REQUIRE(h && h->loaded, "nphm_mlp_query: weights not loaded");
     NPHM_REQUIRE(n_queries >= 1 && n_points >= 0, "nphm_mlp_query: bad sizes");
     NPHM_REQUIRE(cond_dev && (n_points == 0 || (xyz_dev && out_dev)), "nphm_mlp_query: NULL pointer");
-    NPHM_REQUIRE(impl == NPHM_IMPL_AUTO || impl == NPHM_IMPL_SIMT, "nphm_mlp_query: only the SIMT kernel exists for plain MLPs");
+    NPHM_REQUIRE(impl == NPHM_IMPL_AUTO || impl == NPHM_IMPL_SIMT || impl == NPHM_IMPL_TC, "nphm_mlp_query: unknown impl %d", impl);
+    const bool tc_ok = tc_mlp_supported(h) && h->tc_ready;
+    if (impl == NPHM_IMPL_TC && !tc_ok) {
+        set_error("tcgen05 MLP kernel supports only the deformation backbone (hidden 512, 6 layers, condition 232, 3 outputs)");
+        return NPHM_ERR_UNSUPPORTED;
+    }
+    const bool use_tc = impl == NPHM_IMPL_TC || (impl == NPHM_IMPL_AUTO && tc_ok);
     int rc;
     if ((rc = h->cvec.reserve((size_t)n_queries * h->dims.cvec_stride * sizeof(float)))) return rc;
     if ((rc = launch_cvec(h->spec, cond_dev, n_queries, h->cvec.as<float>(), stream))) return rc;
@@ -324,5 +332,6 @@ extern "C" int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *co
     SimtQuery q{};
     q.xyz = xyz_dev; q.total = n_points; q.n_points = n_points; q.n_queries = n_queries; q.quirk_period = 0;
     q.cvec = h->cvec.as<float>(); q.anchors = nullptr; q.blend = 0; q.out = out_dev;
+    if (use_tc) return tc_mlp_launch(h, xyz_dev, h->cvec.as<float>(), n_queries, n_points, out_dev, stream);
     return launch_folded_net(h->net, q, stream);
 }

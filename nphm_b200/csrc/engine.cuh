@@ -63,6 +63,9 @@ struct nphm_mlp {
     nphm::FoldedNet net;
     nphm::PackSpec spec;
     nphm::DeviceBuffer cvec;
+    // tensor-core path (tc_mlp.cu)
+    nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
+    bool tc_ready = false;
 };
 
 namespace nphm {
@@ -71,4 +74,9 @@ int ensemble_prepare(nphm_ensemble *h, const float *latents_dev, int n_queries, 
 bool tc_ensemble_supported(const nphm_ensemble *h);
 int tc_ensemble_pack(nphm_ensemble *h, cudaStream_t stream);
 int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream);
+// tensor-core MLP kernel (tc_mlp.cu): deformation backbone configuration only
+bool tc_mlp_supported(const nphm_mlp *h);
+int tc_mlp_pack(nphm_mlp *h, cudaStream_t stream);
+int tc_mlp_launch(nphm_mlp *h, const float *xyz, const float *cvec, int n_queries, long long n_points, float *out,
+                  cudaStream_t stream);
 }  // namespace nphm

@@ -25,7 +25,7 @@
 //             write the next layer's A operand back to TMEM with tcgen05.st, pre-load D with the next bias.
 // TMEM map (columns): D [0,208)  A_hi [208,312)  A_lo [312,416)   (fp16 pairs, 2 K-values per column).
 #include "engine.cuh"
-#include <cuda_fp16.h>
+#include "tc_common.cuh"
 #include <cstdlib>
 
 namespace nphm {
@@ -41,7 +41,7 @@ constexpr int kSlabBytes = kNP2 * 64;
 constexpr int kGroupBytes = 7 * kSlabBytes;             // weight groups: L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
 constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3Bytes = kKS3 * kSlabBytes;
 constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
-constexpr int kColD = 0, kColAhi = 208, kColAlo = 312, kTmemCols = 512;
+constexpr int kColD = 0, kColAhi = 208, kColAlo = 312;
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
 constexpr int kRecB1 = 832;        // 112
@@ -53,129 +53,6 @@ constexpr int kRecFloats = 1576;
 constexpr int kEpiWarps = 16;      // 4 lane quarters x 4 column groups (8-column chunks dealt round-robin)
 constexpr int kParts = kEpiWarps / 4;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
-constexpr float kS = 144.26950408889634f;            // 100 * log2(e)
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t (&r)[4])
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, no swizzle: 8x(16 B) core matrices of 128 contiguous bytes;
-// LBO = byte distance between the two core matrices along K, SBO = between 8-row groups along N.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46);
-}
-// kind::f16 instruction descriptor: D fp32, A/B fp16, K-major both, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n)
-{
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-// softplus in log2 units: sp'(t) = lg2(1 + 2^t) = max(t, 0) + lg2(1 + 2^-|t|)
-__device__ __forceinline__ float sp_t(float t)
-{
-    float e, l;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-    return fmaxf(t, 0.0f) + l;
-}
-
-// same, with lg2(1 + e) evaluated on the FMA pipe: e * P6(e), |error| < 4.4e-7 (log2 units) on e in [0, 1].
-// Used for every other element so that the MUFU pipe (16 lanes/clk/SM) and the issue slots are balanced.
-__device__ __forceinline__ float sp_t_poly(float t)
-{
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
-    float pl = fmaf(e, 0.015529831517364317f, -0.0795574350973204f);
-    pl = fmaf(pl, e, 0.1942939234405454f);
-    pl = fmaf(pl, e, -0.3259017087892866f);
-    pl = fmaf(pl, e, 0.4735533221244069f);
-    pl = fmaf(pl, e, -0.720585455006072f);
-    pl = fmaf(pl, e, 1.4426678284772665f);
-    return fmaf(pl, e, fmaxf(t, 0.0f));
-}
-// softplus of 8 (4) accumulator values: even elements through MUFU lg2, odd ones through the polynomial
-__device__ __forceinline__ void sp8(const uint32_t (&r)[8], float (&v)[8])
-{
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) { v[e] = sp_t(__uint_as_float(r[e])); v[e + 1] = sp_t_poly(__uint_as_float(r[e + 1])); }
-}
-__device__ __forceinline__ void sp4(const uint32_t (&r)[4], float (&v)[4])
-{
-#pragma unroll
-    for (int e = 0; e < 4; e += 2) { v[e] = sp_t(__uint_as_float(r[e])); v[e + 1] = sp_t_poly(__uint_as_float(r[e + 1])); }
-}
-
-// split two fp32 values into packed fp16 (hi, lo) pairs; element 0 in the low half (lower K index)
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
-{
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
-}
 
 struct __align__(128) Smem {
     uint8_t wbuf[2][kGroupBytes];            // double-buffered weight groups (one bulk copy + one barrier each)
@@ -214,15 +91,6 @@ __device__ __forceinline__ void store_a8(uint32_t tmem_lane_base, int k0, const 
     for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
     tc_st4(tmem_lane_base + kColAhi + (k0 >> 1), hi);
     tc_st4(tmem_lane_base + kColAlo + (k0 >> 1), lo);
-}
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t (&r)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_st2(uint32_t taddr, uint32_t a, uint32_t b)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void store_a4(uint32_t tmem_lane_base, int k0, const float (&v)[4])
 {
@@ -916,5 +784,107 @@ extern "C" int nphm_debug_tc_mma_bench(int n, int iters, int alternate, long lon
     cudaError_t e = cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { set_error("nphm_debug_tc_mma_bench: %s", cudaGetErrorString(e)); return NPHM_ERR_CUDA; }
+    return NPHM_OK;
+}
+
+// Layout probe for M = 64, A and B both from shared memory (SS form): D[64 x n] = A[64 x 16*ks] * B[n x 16*ks]^T.
+// A is stored K-chunk-major (for each 8-column K chunk: 64 rows x 16 B contiguous; LBO = 1024 B, SBO = 128 B), hi plane
+// then lo plane.  The whole TMEM accumulator region (128 lanes x n columns) is dumped so the host can recover the
+// row -> lane mapping.
+namespace nphm { namespace tc {
+__global__ void __launch_bounds__(160, 1) mma_m64_probe_kernel(const float *__restrict__ A, const uint8_t *__restrict__ slabs,
+                                                               int n, int ks, int variant, float *__restrict__ dump)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slab_bytes = n * 64;
+    uint8_t *a_hi = smem_raw, *a_lo = smem_raw + ks * 4096, *b_base = smem_raw + ks * 8192;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ks * slab_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(b_base)[i] = reinterpret_cast<const uint4 *>(slabs)[i];
+    const int m_rows = (variant & 8) ? 128 : 64;
+    const int vlay = variant & 3;
+    if (threadIdx.x < m_rows) {
+        const int row = threadIdx.x;
+        for (int kc = 0; kc < ks * 2; ++kc) {            // 8-column K chunks
+            uint32_t hi[4], lo[4];
+            for (int i = 0; i < 4; ++i) split2(A[(size_t)row * ks * 16 + kc * 8 + 2 * i], A[(size_t)row * ks * 16 + kc * 8 + 2 * i + 1], hi[i], lo[i]);
+            // variant 0/1: K-chunk-major (chunk kc: 64 rows x 16 B); variant 2: like the B slabs (row-group-major per k-step)
+            const size_t off = vlay == 2 ? (size_t)(kc >> 1) * (m_rows * 32) + (size_t)(row >> 3) * 256 + (size_t)(kc & 1) * 128 + (size_t)(row & 7) * 16
+                                         : (size_t)kc * (m_rows * 16) + (size_t)row * 16;
+            *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (warp < 4) {
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t fill[8];
+        for (int e = 0; e < 8; ++e) fill[e] = __float_as_uint(0.f);
+        for (int c = 0; c < n; c += 8) tc_st8(tl + c, fill);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 128) {
+        const int m_rows2 = (variant & 8) ? 128 : 64;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m_rows2 >> 4) << 24);
+        for (int j = 0; j < ks; ++j) {
+            const uint32_t albo = (variant & 3) == 2 ? 128 : m_rows2 * 16, asbo = (variant & 3) == 2 ? 256 : 128;
+            const uint32_t astep = m_rows2 * 32;
+            uint64_t ah = make_desc(smem_u32(a_hi + j * astep), albo, asbo), al = make_desc(smem_u32(a_lo + j * astep), albo, asbo);
+            const uint32_t b = smem_u32(b_base + (size_t)j * slab_bytes);
+            uint64_t bh = make_desc(b, 128, 256), bl = make_desc(b + n * 32, 128, 256);
+            if (variant & 4) { uint64_t t = ah; ah = bh; bh = t; t = al; al = bl; bl = t; }      // swap operand order
+            tc_mma_ss(tmem, ah, bh, idesc, 1);
+            tc_mma_ss(tmem, ah, bl, idesc, 1);
+            tc_mma_ss(tmem, al, bh, idesc, 1);
+        }
+        tc_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    if (warp < 4) {
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < n; c += 8) {
+            uint32_t r[8];
+            tc_ld8(tl + c, r);
+            tc_wait_ld();
+            for (int e = 0; e < 8; ++e) dump[(size_t)(warp * 32 + lane) * n + c + e] = __uint_as_float(r[e]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+}}
+extern "C" int nphm_debug_tc_mma_m64(const float *a_dev, const float *b_dev, int n, int ks, int variant, float *dump_dev, void *stream_)
+{
+    using namespace nphm;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && ks >= 1 && ks <= 8, "nphm_debug_tc_mma_m64: bad shape");
+    uint8_t *slabs = nullptr;
+    NPHM_CUDA_CHECK(cudaMalloc(&slabs, (size_t)ks * n * 64));
+    tc::pack_test_slabs_kernel<<<64, 256, 0, stream>>>(b_dev, n, ks, slabs);
+    const int smem = ks * 8192 + ks * n * 64 + 1024;
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(tc::mma_m64_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::mma_m64_probe_kernel<<<1, 160, smem, stream>>>(a_dev, slabs, n, ks, variant, dump_dev);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(slabs);
+    if (e != cudaSuccess) { set_error("nphm_debug_tc_mma_m64: %s", cudaGetErrorString(e)); return NPHM_ERR_CUDA; }
     return NPHM_OK;
 }

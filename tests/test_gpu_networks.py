@@ -204,3 +204,30 @@ def test_pruned_kernel_is_opt_in_and_within_its_error_bound(cuda_device):
         x = torch.from_numpy(g['points_' + tag]).to(cuda_device).unsqueeze(0)
         s, _ = eng.query(x, lat.reshape(1, -1), eval_quirk=True, impl='tc_pruned')       # explicit points (no blocks)
         assert np.abs(s.cpu().numpy().reshape(-1) - g['sdf_eval_' + tag]).max() < TOL
+
+
+def test_deformation_tensor_core_kernel(cuda_device):
+    """tcgen05 MLP kernel (M=64 tiles, A in shared memory) against the reference golden, the oracle and the FFMA kernel."""
+    d = load_golden('deform.npz')
+    dfn = make_deformation(cuda_device)
+    eng = dfn.defDeepSDF.engine()
+    pts = torch.from_numpy(d['points']).to(cuda_device).unsqueeze(0)
+    cond_id = torch.cat([torch.from_numpy(d['latent_id']), torch.from_numpy(d['z_ex'])]).reshape(1, 1, -1).to(cuda_device)
+    anc = torch.from_numpy(d['anchors']).to(cuda_device).unsqueeze(0)
+    with torch.no_grad():
+        cond = dfn._condition(pts, cond_id, anc, per_point=False)[:, 0]
+    tc = eng.query(pts, cond, impl='tc')
+    simt = eng.query(pts, cond, impl='simt')
+    e_gold = np.abs(tc.cpu().numpy()[0] - d['offsets']).max()
+    e_simt = (tc - simt).abs().max().item()
+    print('deformation tc: max abs err vs reference golden %.3g, vs FFMA kernel %.3g' % (e_gold, e_simt))
+    assert e_gold < TOL and e_simt < 2e-6
+    # ragged sizes and a batch of queries with different conditions
+    rng = np.random.RandomState(3)
+    mp = O.MlpParams(sd_numpy(dfn), prefix='defDeepSDF.')
+    for n in (1, 63, 64, 65, 1000):
+        x = (rng.rand(2, n, 3) - 0.5).astype(np.float32)
+        c = (rng.randn(2, 232) * 0.3).astype(np.float32)
+        got = eng.query(torch.from_numpy(x).to(cuda_device), torch.from_numpy(c).to(cuda_device), impl='tc').cpu().numpy()
+        for b in range(2):
+            assert np.abs(got[b] - O.mlp_forward(mp, x[b], c[b])).max() < TOL, n

@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--res', type=int, default=128)
     ap.add_argument('--fit-iters', type=int, default=200)
+    ap.add_argument('--joint-res', type=int, default=256)
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     out = {}
@@ -40,6 +41,24 @@ def main():
     n = pts.shape[1]
     out['deformation_query'] = {'res': args.res, 'ms': ms, 'points_per_s': n / (ms * 1e-3),
                                 'tflops_dense': 2.624e6 * n / (ms * 1e-3) / 1e12}
+    # ---- joint query (BASELINE.json configs[2]): identity SDF + forward deformation on the same grid
+    R = args.joint_res
+    gp = torch.from_numpy(create_grid_points_from_bounds(MINI, MAXI, R)).to(dev, dtype=torch.float).reshape(1, -1, 3)
+    vol = torch.empty(R ** 3, device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            dec.engine().query_grid(lat, MINI, MAXI, R, 0, R ** 3, 25000, out=vol)
+            off, _ = dfn(gp, cond, anchors)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            dec.engine().query_grid(lat, MINI, MAXI, R, 0, R ** 3, 25000, out=vol)
+            off, _ = dfn(gp, cond, anchors)
+        e1.record(); torch.cuda.synchronize()
+    jms = e0.elapsed_time(e1) / 3
+    out['joint_query'] = {'res': R, 'ms': jms, 'points_per_s': R ** 3 / (jms * 1e-3),
+                          'tflops_dense': 12.24e6 * R ** 3 / (jms * 1e-3) / 1e12}
+    del gp, off
     # ---- identity fitting: 5 x 1000 points per iteration
     rng = np.random.RandomState(0)
     obs = torch.from_numpy((rng.randn(5000, 3) * 0.12).astype(np.float32)).to(dev)
