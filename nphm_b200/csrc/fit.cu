@@ -25,7 +25,7 @@ namespace fit {
 
 constexpr int TM = 2;
 constexpr int P = 32 * TM;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 
 struct Dims {
     int n_members, n_symm, n_loc;
