@@ -42,6 +42,9 @@ constexpr int kGroupBytes = 7 * kSlabBytes;             // weight groups: L1 | L
 constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3Bytes = kKS3 * kSlabBytes;
 constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
 constexpr int kColD = 0, kColAhi = 208, kColAlo = 312;
+// spare columns: first 96 K values (hi | lo) of layer 1's A operand, written ahead of time for the NEXT member
+constexpr int kColSpareHi = 416, kColSpareLo = 464, kNA = 96;
+constexpr int kRecSlots = 3;
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
 constexpr int kRecB1 = 832;        // 112
@@ -56,10 +59,10 @@ constexpr int kThreads = 32 * (kEpiWarps + 2);
 
 struct __align__(128) Smem {
     uint8_t wbuf[2][kGroupBytes];            // double-buffered weight groups (one bulk copy + one barrier each)
-    float rec[2][kRecFloats];
+    float rec[kRecSlots][kRecFloats];
     float partial[kParts - 1][128];
     uint64_t w_full[2], w_empty[2];
-    uint64_t rec_full[2], rec_empty[2];
+    uint64_t rec_full[kRecSlots], rec_empty[kRecSlots];
     uint64_t a_ready, d_ready, mask_ready;
     unsigned long long maskq[2][4];
     uint32_t tmem_base;
@@ -125,10 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     const long long n_tiles = p.n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1);
-            mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps);
-        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+        for (int i = 0; i < kRecSlots; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps); }
         mbar_init(&sm.a_ready, kEpiWarps);
         mbar_init(&sm.d_ready, 1);
         mbar_init(&sm.mask_ready, 4);
@@ -147,11 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     if (warp == kEpiWarps) {
         // =========================================================================== producer (bulk async copies)
         if (lane == 0) {
-            int wb = 0, rslot = 0;
-            uint32_t wph = 0, rph = 0, tcount = 0;
+            int wb = 0;
+            uint32_t wph = 0, tcount = 0, rcount = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 const int qi = (int)(tile / tiles_per_query);
-                unsigned long long mask = ~0ull;
+                unsigned long long mask = (1ull << p.n_members) - 1;
                 if (PRUNE) {
                     mbar_wait(&sm.mask_ready, tcount & 1);
                     const unsigned long long *mq = sm.maskq[tcount & 1];
@@ -159,11 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 }
                 for (int m = 0; m < p.n_members; ++m) {
                     if (PRUNE && !((mask >> m) & 1)) continue;
-                    mbar_wait(&sm.rec_empty[rslot], rph ^ 1);
-                    mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
-                    bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
-                             &sm.rec_full[rslot]);
-                    if (++rslot == 2) { rslot = 0; rph ^= 1; }
+                    {
+                        const int rslot = rcount % kRecSlots;
+                        mbar_wait(&sm.rec_empty[rslot], ((rcount / kRecSlots) & 1) ^ 1);
+                        mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
+                        bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
+                                 &sm.rec_full[rslot]);
+                        ++rcount;
+                    }
                     const int set = m < 2 * p.n_symm ? (m >> 1) : m - p.n_symm;
                     const uint8_t *w = p.weights + (size_t)set * kSetBytes;
 #pragma unroll 1
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
             int wb = 0;
             uint32_t wph = 0, a_ph = 0, tcount = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                unsigned long long mask = ~0ull;
+                unsigned long long mask = (1ull << p.n_members) - 1;
                 if (PRUNE) {
                     mbar_wait(&sm.mask_ready, tcount & 1);
                     const unsigned long long *mq = sm.maskq[tcount & 1];
@@ -211,7 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                             const uint32_t slab = base + j * n * 64;
                             const uint64_t b_hi = make_desc(slab, 128, 256);
                             const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
-                            const uint32_t a_hi = tmem + kColAhi + (k0 + j) * 8, a_lo = tmem + kColAlo + (k0 + j) * 8;
+                            const bool spare = g == 0 && j < kNA / 16;
+                            const uint32_t a_hi = tmem + (spare ? kColSpareHi : kColAhi) + (k0 + j) * 8;
+                            const uint32_t a_lo = tmem + (spare ? kColSpareLo : kColAlo) + (k0 + j) * 8;
                             tc_mma_ts(tmem + kColD, a_hi, b_hi, idesc, 1);
                             tc_mma_ts(tmem + kColD, a_hi, b_lo, idesc, 1);
                             tc_mma_ts(tmem + kColD, a_lo, b_hi, idesc, 1);
@@ -229,8 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         const int q = warp & 3, part = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
-        int rslot = 0;
-        uint32_t rph = 0, d_ph = 0, tcount = 0;
+        uint32_t d_ph = 0, tcount = 0, rcount = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             int qi;
             long long idx, g;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
             }
             const bool quirk = p.quirk_period > 0 && ((g % p.quirk_period) == p.quirk_period - 1 || g == p.total - 1);
             float num = 0.f, den = 0.f;
-            unsigned long long mask = ~0ull;
+            unsigned long long mask = (1ull << p.n_members) - 1;
             if (PRUNE) {
                 // blend weights of all members for this thread's point: S = sum_k w_k; a member is needed by the tile if
                 // w_k >= tau * (S + 1e-6) for at least one of its points (dropped mass per point < n_members * tau).
@@ -304,14 +309,42 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 mask = mq[0] | mq[1] | mq[2] | mq[3];
             }
 
+            // first 96 layer-0 outputs (chunks part, part+4, part+8) -> spare TMEM columns.  Normally computed for the NEXT
+            // member while the current member's layer-3 MMAs run; at the start of a tile it is computed in place.
+            auto layer0_a = [&](const float *r, float ccx, float ccy, float ccz) {
+                const float4 *l0a = reinterpret_cast<const float4 *>(r + kRecL0);
+#pragma unroll 1
+                for (int c = part; c < 12; c += kParts) {
+                    const int n0 = c * 8;
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 w = l0a[n0 + e];
+                        const float t = fmaf(w.x, ccx, fmaf(w.y, ccy, fmaf(w.z, ccz, w.w)));
+                        v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                    tc_st4(tl + kColSpareHi + (n0 >> 1), hi);
+                    tc_st4(tl + kColSpareLo + (n0 >> 1), lo);
+                }
+            };
+            auto member_coords = [&](const float *r, float &ccx, float &ccy, float &ccz) {
+                ccx = x - r[kRecMisc + 1]; ccy = y - r[kRecMisc + 2]; ccz = z - r[kRecMisc + 3];
+                if (r[kRecMisc + 5] != 0.f) ccx = -ccx;          // mirrored member
+                ccx *= kS; ccy *= kS; ccz *= kS;                // coordinates in log2 units
+            };
+            bool a_done = false;
+
             for (int m = 0; m < p.n_members; ++m) {
-                if (PRUNE && !((mask >> m) & 1)) continue;
-                mbar_wait(&sm.rec_full[rslot], rph);
+                if (!((mask >> m) & 1)) continue;
+                const int rslot = rcount % kRecSlots;
+                mbar_wait(&sm.rec_full[rslot], (rcount / kRecSlots) & 1);
                 const float *rec = sm.rec[rslot];
                 const float ax = rec[kRecMisc + 1], ay = rec[kRecMisc + 2], az = rec[kRecMisc + 3];
-                float cx = x - ax, cy = y - ay, cz = z - az;
-                if (rec[kRecMisc + 5] != 0.f) cx = -cx;          // mirrored member
-                cx *= kS; cy *= kS; cz *= kS;                   // coordinates in log2 units
+                float cx, cy, cz;
+                member_coords(rec, cx, cy, cz);
 
                 // Column ownership (balanced: 6.5 chunks per warp and layer): 8-column chunks c = part + 4i (i < 6)
                 // cover columns 0..191, the 4-column piece 192 + 4*part covers 192..207; for the 112-column layer 1:
@@ -320,8 +353,11 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
 
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1; D preloaded with S*b1
+                if (!a_done) layer0_a(rec, cx, cy, cz);
 #pragma unroll 1
-                for (int c = part; c < 24; c += kParts) {
+                for (int c = part; c < 12; c += kParts) init_d8(tl, c * 8, rec + kRecB1);
+#pragma unroll 1
+                for (int c = 12 + part; c < 24; c += kParts) {
                     const int n0 = c * 8;
                     float v[8];
 #pragma unroll
@@ -331,7 +367,6 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
                     store_a8(tl, n0, v);
-                    if (c < 12) init_d8(tl, n0, rec + kRecB1);
                 }
                 {
                     const int n0 = 192 + 4 * part;               // rows >= 200 are zero: sp(0) meets zero weights
@@ -415,6 +450,20 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.a_ready);
 
+                // ---------------- in the shadow of the layer-3 MMAs: first part of layer 0 of the next member of this tile
+                {
+                    const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
+                    a_done = rest != 0;
+                    if (a_done) {
+                        const uint32_t nslot = (rcount + 1) % kRecSlots;
+                        mbar_wait(&sm.rec_full[nslot], ((rcount + 1) / kRecSlots) & 1);
+                        const float *nrec = sm.rec[nslot];
+                        float nx, ny, nz;
+                        member_coords(nrec, nx, ny, nz);
+                        layer0_a(nrec, nx, ny, nz);
+                    }
+                }
+
                 // ---------------- epilogue of layer 3 fused with the output layer (dot with w4) and the blend
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
@@ -468,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.rec_empty[rslot]);
-                if (++rslot == 2) { rslot = 0; rph ^= 1; }
+                ++rcount;
             }
             if (part == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
         }
