@@ -8,6 +8,9 @@ namespace tc {
 
 constexpr float kS = 144.26950408889634f;            // 100 * log2(e)
 constexpr int kTmemCols = 512;
+#ifndef NPHM_POLY_MASK
+#define NPHM_POLY_MASK 0xAA          // which of 8 consecutive elements evaluate lg2(1+e) on the FMA pipe (bit set) vs MUFU
+#endif
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,7 +116,7 @@ __device__ __forceinline__ float sp_t_poly(float t)
 __device__ __forceinline__ void sp8(const uint32_t (&r)[8], float (&v)[8])
 {
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) { v[e] = sp_t(__uint_as_float(r[e])); v[e + 1] = sp_t_poly(__uint_as_float(r[e + 1])); }
+    for (int e = 0; e < 8; ++e) v[e] = (NPHM_POLY_MASK >> e) & 1 ? sp_t_poly(__uint_as_float(r[e])) : sp_t(__uint_as_float(r[e]));
 }
 __device__ __forceinline__ void sp4(const uint32_t (&r)[4], float (&v)[4])
 {
