@@ -37,7 +37,7 @@ from NPHM.models.EnsembledDeepSDF import FastEnsembleDeepSDFMirrored     # noqa:
 from NPHM.models.deepSDF import DeepSDF, DeformationNetwork              # noqa: E402
 from NPHM.models.reconstruction import get_logits                        # noqa: E402
 from NPHM.utils.reconstruction import create_grid_points_from_bounds     # noqa: E402
-from NPHM.models.fitting import inference_identity_space                 # noqa: E402
+from NPHM.models.fitting import inference_identity_space, inference_iterative_root_finding_joint   # noqa: E402
 
 MINI = [-.55, -.5, -.95]
 MAXI = [0.55, 0.75, 0.4]
@@ -185,6 +185,57 @@ def main():
     traj['lrs'] = np.array(record['lr'], np.float64)
     print('fit', n_iter, 'iters: |z| =', float(z.detach().norm()), 'grad norms', np.linalg.norm(traj['grads'], axis=1)[:4])
     np.savez_compressed(os.path.join(HERE, 'fit_identity.npz'), obs=np.stack(obs), **traj)
+
+    # ---------------------------------------------------------------- joint fitting (identity + expression, Broyden)
+    # inference_iterative_root_finding_joint hard-codes `.cuda()` on two index tensors (fitting.py:72,137); to run the
+    # UNMODIFIED function on this CPU-only box Tensor.cuda is patched to the identity for the duration of the call.
+    rng = np.random.RandomState(200)
+    obs_j = [(rng.randn(200, 3) * 0.1 + np.array([0.0, 0.05, -0.1])).astype(np.float32) for _ in range(3)]
+    rec = {'grads': [], 'params': []}
+
+    class RecordingAdam2(real_adam):
+        def step(self, closure=None):
+            p_ = self.param_groups[0]['params'][0]
+            rec['grads'].append(p_.grad.detach().clone().numpy().copy())
+            rec['params'].append(p_.detach().clone().numpy().copy())
+            return super().step(closure)
+
+    optim_mod.Adam = RecordingAdam2
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        dec = make_ensemble(0, anchors)
+        dec.train()
+        torch.manual_seed(10)
+        dfn = DeformationNetwork(mode='compress', lat_dim_expr=200, lat_dim_id=32, lat_dim_glob_shape=64,
+                                 lat_dim_loc_shape=32, n_loc=39, anchors=anchors, hidden_dim=512, nlayers=6,
+                                 out_dim=3, input_dim=3)
+        dfn.eval()                                                      # fitting_pointclouds.py:229
+        lambdas = {'surface': 2.0, 'reg_expr': 0.01, 'reg_global': 0.25, 'reg_unobserved': 10, 'reg_loc': 0.05,
+                   'symm_dist': 5.0}                                    # fitting_pointclouds.py:253-259
+        schedule = {'lr': {200: 2, 400: 2, 600: 2, 800: 2}, 'symm_dist': {200: 10, 500: 9999},
+                    'reg_glob': {200: 3, 600: 10}, 'reg_loc': {500: 3, 600: 10}, 'reg_expr': {600: 10}}
+        np.random.seed(0)
+        torch.manual_seed(0)
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            z_ex, z_id, anc = inference_iterative_root_finding_joint(dec, dfn, [torch.from_numpy(o) for o in obs_j],
+                                                                     lambdas, n_steps=400, schedule_cfg=schedule,
+                                                                     step_scale=0.01)
+    finally:
+        optim_mod.Adam = real_adam
+        torch.Tensor.cuda = real_cuda
+    # opt.step() (identity) is called before opt_expr.step(): records alternate id, expr, id, expr ...
+    np.savez_compressed(os.path.join(HERE, 'fit_joint.npz'), obs=np.stack(obs_j),
+                        z_id_final=z_id.detach().numpy().reshape(-1), z_ex_final=z_ex.detach().numpy().reshape(3, 200),
+                        anchors_final=anc.detach().numpy().reshape(39, 3),
+                        grads_id=np.stack([g.reshape(-1) for g in rec['grads'][0::2]]),
+                        grads_ex=np.stack([g.reshape(3, 200) for g in rec['grads'][1::2]]),
+                        z_id_before=np.stack([g.reshape(-1) for g in rec['params'][0::2]]),
+                        z_ex_before=np.stack([g.reshape(3, 200) for g in rec['params'][1::2]]))
+    print('joint fit: 4 iterations, |z_id| %.4f |z_ex| %.4f, grad norms id %s' % (
+        float(z_id.detach().norm()), float(z_ex.detach().norm()),
+        [round(float(np.linalg.norm(g)), 4) for g in rec['grads'][0::2]]))
 
 
 if __name__ == '__main__':

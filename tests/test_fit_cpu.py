@@ -57,3 +57,30 @@ def test_autograd_fallback_follows_reference():
     close = np.abs(z.detach().numpy().reshape(-1) - ref) < 2e-4
     # Adam's first steps are sign-like: elements whose gradient is at round-off level may differ
     assert close.mean() > 0.98, close.mean()
+
+
+def _joint_setup():
+    from conftest import make_deformation
+    g = load_golden('fit_joint.npz')
+    lambdas = {'surface': 2.0, 'reg_expr': 0.01, 'reg_global': 0.25, 'reg_unobserved': 10, 'reg_loc': 0.05,
+               'symm_dist': 5.0}
+    schedule = {'lr': {200: 2, 400: 2, 600: 2, 800: 2}, 'symm_dist': {200: 10, 500: 9999},
+                'reg_glob': {200: 3, 600: 10}, 'reg_loc': {500: 3, 600: 10}, 'reg_expr': {600: 10}}
+    return g, lambdas, schedule, make_deformation
+
+
+def test_joint_fitter_mirror_follows_reference():
+    """2 iterations of inference_iterative_root_finding_joint (Broyden correspondences + implicit differentiation)
+    through the mirrored modules on CPU, against the latents the reference produced."""
+    from nphm_b200.models.fitting import inference_iterative_root_finding_joint
+    g, lambdas, schedule, make_deformation = _joint_setup()
+    dec = make_ensemble(0).train()
+    dfn = make_deformation()
+    np.random.seed(0)
+    torch.manual_seed(0)
+    z_ex, z_id, anchors = inference_iterative_root_finding_joint(dec, dfn, [torch.from_numpy(o) for o in g['obs']], lambdas,
+                                                                 n_steps=200, schedule_cfg=schedule, step_scale=0.01)
+    assert z_ex.shape == (3, 1, 200) and z_id.shape == (1, 1, 1344) and anchors.shape == (1, 39, 3)
+    close_id = np.abs(z_id.detach().numpy().reshape(-1) - g['z_id_before'][2]) < 2e-4
+    close_ex = np.abs(z_ex.detach().numpy().reshape(3, 200) - g['z_ex_before'][2]) < 2e-4
+    assert close_id.mean() > 0.97 and close_ex.mean() > 0.97, (close_id.mean(), close_ex.mean())

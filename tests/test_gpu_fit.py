@@ -74,3 +74,30 @@ def test_inference_identity_space_dropin(cuda_device):
           % (100 * close.mean(), np.abs(zf - g['z_final']).max()))
     assert close.mean() > 0.95
     assert np.abs(anchors.cpu().numpy()[0] - g['anchors_final']).max() < 2e-3
+
+
+def test_joint_fitter_on_gpu_follows_reference(cuda_device):
+    """The joint fitter on the GPU: Broyden's no-grad network evaluations run on the fused tensor-core MLP kernel, the
+    loss/backward part on autograd through the composite modules.  4 iterations against the reference's latents."""
+    from conftest import make_deformation
+    from nphm_b200.models.fitting import inference_iterative_root_finding_joint
+    g = load_golden('fit_joint.npz')
+    lambdas = {'surface': 2.0, 'reg_expr': 0.01, 'reg_global': 0.25, 'reg_unobserved': 10, 'reg_loc': 0.05,
+               'symm_dist': 5.0}
+    schedule = {'lr': {200: 2, 400: 2, 600: 2, 800: 2}, 'symm_dist': {200: 10, 500: 9999},
+                'reg_glob': {200: 3, 600: 10}, 'reg_loc': {500: 3, 600: 10}, 'reg_expr': {600: 10}}
+    dec = make_ensemble(0, device=cuda_device).train()
+    dfn = make_deformation(cuda_device)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    z_ex, z_id, anchors = inference_iterative_root_finding_joint(
+        dec, dfn, [torch.from_numpy(o).to(cuda_device) for o in g['obs']], lambdas, n_steps=400, schedule_cfg=schedule,
+        step_scale=0.01)
+    zi = z_id.detach().cpu().numpy().reshape(-1)
+    ze = z_ex.detach().cpu().numpy().reshape(3, 200)
+    ci = (np.abs(zi - g['z_id_final']) < 5e-4).mean()
+    ce = (np.abs(ze - g['z_ex_final']) < 5e-4).mean()
+    print('joint fit on GPU: %.1f%% of z_id and %.1f%% of z_ex entries within 5e-4 of the reference after 4 iterations'
+          % (100 * ci, 100 * ce))
+    assert ci > 0.9 and ce > 0.9
+    assert np.abs(anchors.detach().cpu().numpy()[0] - g['anchors_final']).max() < 2e-3
