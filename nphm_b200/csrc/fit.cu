@@ -450,8 +450,22 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
     dim3 grid(tiles, h->n_members);
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_member_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_member_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fit::fit_member_kernel<false><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
-    NPHM_CUDA_CHECK(cudaGetLastError());
+    if (tc_ensemble_supported(h) && h->tc_ready) {
+        // forward pass on the tensor-core kernel: member outputs s_k -> member_s (the blended output is recomputed by
+        // fit_blend_kernel together with the loss bookkeeping)
+        SimtQuery q{};
+        q.xyz = points_dev; q.first = 0; q.total = n_points; q.n_points = n_points; q.n_queries = 1; q.quirk_period = 0;
+        q.cvec = h->cvec.as<float>(); q.anchors = h->anchors.as<float>(); q.blend = 1;
+        q.out = b.out; q.members_out = b.member_s;
+        const bool saved_prune = h->tc_prune;
+        h->tc_prune = false;
+        rc = tc_ensemble_launch(h, q, stream);
+        h->tc_prune = saved_prune;
+        if (rc) return rc;
+    } else {
+        fit::fit_member_kernel<false><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
+        NPHM_CUDA_CHECK(cudaGetLastError());
+    }
     fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
     NPHM_CUDA_CHECK(cudaGetLastError());
     fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);

@@ -17,6 +17,7 @@ struct SimtQuery {
     const float *anchors;     // [n_queries][n_members-1][3] (ensemble) or nullptr (plain MLP)
     int blend;                // 1: Gaussian anchor blend of member outputs (ensemble); 0: write channels
     float *out;
+    float *members_out;       // optional (tensor-core kernel only): un-blended member outputs [q][point][member]
 };
 
 // description of the reference-layout parameters, used by the packing / cvec kernels

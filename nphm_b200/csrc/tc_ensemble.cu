@@ -78,6 +78,7 @@ struct Params {
     int n_queries;
     long long quirk_period;
     float *out;
+    float *members_out;         // optional [n_queries][n_points][n_members]: un-blended member outputs s_k (fitting)
     int n_members, n_symm;
     // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
     const float *anchors;       // [n_queries][n_members-1][3]
@@ -503,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     float s = acc + rec[kRecMisc + 0];
 #pragma unroll
                     for (int i = 0; i < kParts - 1; ++i) s += sm.partial[i][row];
+                    if (p.members_out && valid) p.members_out[((size_t)qi * p.n_points + idx) * p.n_members + m] = s;
                     float d;
                     if (rec[kRecMisc + 4] != 0.f) {
                         const float dx = ax - x, dy = ay - y, dz = az - z;
@@ -736,7 +738,7 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.weights = h->tc_weights.as<uint8_t>();
     p.recs = h->tc_consts.as<float>();
     p.xyz = q.xyz; p.axes = q.axes; p.res = q.res; p.first = q.first; p.total = q.total; p.n_points = q.n_points;
-    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out;
+    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out; p.members_out = q.members_out;
     p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
     const bool prune = h->tc_prune;
     p.anchors = q.anchors; p.prune_tau = h->tc_prune_tau;
