@@ -119,6 +119,21 @@ int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, const float *c
 int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries,
                    long long n_points, float *out_dev, int impl, void *stream);
 
+/* Batched Broyden search for canonical correspondences: roots of  x + F(x; cond) - obs  per point, F = this MLP
+ * (3 outputs).  Replaces the Python loop of models/iterative_root_finding.py:5-71 (`broyden`) with the residual of
+ * `search` (:142-147): same update rule, thresholds and freeze logic, one fused-MLP launch per step, no host
+ * round trips except a 4-byte "still active?" read every 3 steps (the reference's early exit).
+ *   x_dev          in: start points, out: 'result' (n_queries*n_points*3) - like the reference this is the point at
+ *                  which a sample stopped, not the best one seen (its x_opt aliases x)
+ *   jinv_init_dev  n_queries*n_points*9 row-major initial inverse Jacobians (not modified)
+ *   diff_dev       out: smallest residual norm seen per sample; valid_dev out: diff < cvg_thresh (1 byte each)
+ *   steps_done     host int, may be NULL.  workspace_dev: nphm_broyden_workspace_bytes(n_queries*n_points) bytes. */
+long long nphm_broyden_workspace_bytes(long long n_total);
+int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n_queries, long long n_points,
+                            const float *obs_dev, float *x_dev, const float *jinv_init_dev, int max_steps,
+                            float cvg_thresh, float dvg_thresh, float eps, float *diff_dev,
+                            unsigned char *valid_dev, int *steps_done, void *workspace_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Marching cubes == mcubes.marching_cubes(volume, iso) as called at utils/reconstruction.py:30
  * (PyMCubes semantics restated in oracle/mc_oracle.c: x-major cell order, `<=` classification, one vertex per

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
     'nphm_fit_workspace_bytes', 'nphm_fit_identity_step',
+    'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search',
 )
 
 
@@ -107,6 +108,11 @@ def lib() -> ctypes.CDLL:
     L.nphm_fit_workspace_bytes.restype = c_longlong
     L.nphm_fit_identity_step.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                          POINTER(FitParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.nphm_broyden_workspace_bytes.argtypes = [c_longlong]
+    L.nphm_broyden_workspace_bytes.restype = c_longlong
+    L.nphm_mlp_broyden_search.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
+                                          c_float, c_float, c_float, c_void_p, c_void_p, POINTER(c_int), c_void_p,
+                                          c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is c_int and name not in ('nphm_abi_version',):
@@ -317,6 +323,28 @@ class MlpEngine(_Versioned):
                                        _mlp_impl(impl), _stream_ptr(dev)),
                   'nphm_mlp_query')
         return out
+
+    def broyden_search(self, obs: torch.Tensor, cond: torch.Tensor, x_init: torch.Tensor, J_inv_init: torch.Tensor,
+                       max_steps: int = 15, cvg_thresh: float = 1e-6, dvg_thresh: float = 0.2, eps: float = 1e-6):
+        """Roots of ``x + F(x; cond) - obs`` by the reference's Broyden iteration, entirely on the device.
+        obs, x_init: B x N x 3, cond: B x lat_dim, J_inv_init: B x N x 3 x 3.
+        Returns ``(x B x N x 3, diff B x N, valid B x N bool, steps taken)``."""
+        B, N, _ = obs.shape
+        dev = obs.device
+        obs = _f32c(obs)
+        cond = _f32c(cond).to(dev)
+        x = _f32c(x_init).clone()
+        jinv = _f32c(J_inv_init.reshape(B, N, 9))
+        diff = torch.empty(B, N, device=dev, dtype=torch.float32)
+        valid = torch.empty(B, N, device=dev, dtype=torch.uint8)
+        steps = c_int(0)
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(int(lib().nphm_broyden_workspace_bytes(B * N)), 256), device=dev, dtype=torch.uint8)
+            check(lib().nphm_mlp_broyden_search(self._h, cond.data_ptr(), B, N, obs.data_ptr(), x.data_ptr(),
+                                                jinv.data_ptr(), int(max_steps), float(cvg_thresh), float(dvg_thresh),
+                                                float(eps), diff.data_ptr(), valid.data_ptr(), byref(steps),
+                                                ws.data_ptr(), _stream_ptr(dev)), 'nphm_mlp_broyden_search')
+        return x, diff, valid.bool(), steps.value
 
 
 # ------------------------------------------------------------------------------------------ marching cubes

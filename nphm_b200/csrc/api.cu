@@ -311,6 +311,28 @@ extern "C" int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, con
     return NPHM_OK;
 }
 
+namespace nphm {
+// folded constants of the condition (one row per query); must precede mlp_run on the same stream
+int mlp_prepare(nphm_mlp *h, const float *cond_dev, int n_queries, cudaStream_t stream)
+{
+    int rc;
+    if ((rc = h->cvec.reserve((size_t)n_queries * h->dims.cvec_stride * sizeof(float)))) return rc;
+    return launch_cvec(h->spec, cond_dev, n_queries, h->cvec.as<float>(), stream);
+}
+
+// point pass with the constants of the last mlp_prepare; impl AUTO = tensor-core kernel when the shape allows it
+int mlp_run(nphm_mlp *h, const float *xyz_dev, int n_queries, long long n_points, float *out_dev, int impl, cudaStream_t stream)
+{
+    if (n_points == 0) return NPHM_OK;
+    const bool use_tc = impl == NPHM_IMPL_TC || (impl == NPHM_IMPL_AUTO && tc_mlp_supported(h) && h->tc_ready);
+    if (use_tc) return tc_mlp_launch(h, xyz_dev, h->cvec.as<float>(), n_queries, n_points, out_dev, stream);
+    SimtQuery q{};
+    q.xyz = xyz_dev; q.total = n_points; q.n_points = n_points; q.n_queries = n_queries; q.quirk_period = 0;
+    q.cvec = h->cvec.as<float>(); q.anchors = nullptr; q.blend = 0; q.out = out_dev;
+    return launch_folded_net(h->net, q, stream);
+}
+}  // namespace nphm
+
 extern "C" int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries,
                               long long n_points, float *out_dev, int impl, void *stream_)
 {
@@ -326,12 +348,6 @@ extern "C" int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *co
     }
     const bool use_tc = impl == NPHM_IMPL_TC || (impl == NPHM_IMPL_AUTO && tc_ok);
     int rc;
-    if ((rc = h->cvec.reserve((size_t)n_queries * h->dims.cvec_stride * sizeof(float)))) return rc;
-    if ((rc = launch_cvec(h->spec, cond_dev, n_queries, h->cvec.as<float>(), stream))) return rc;
-    if (n_points == 0) return NPHM_OK;
-    SimtQuery q{};
-    q.xyz = xyz_dev; q.total = n_points; q.n_points = n_points; q.n_queries = n_queries; q.quirk_period = 0;
-    q.cvec = h->cvec.as<float>(); q.anchors = nullptr; q.blend = 0; q.out = out_dev;
-    if (use_tc) return tc_mlp_launch(h, xyz_dev, h->cvec.as<float>(), n_queries, n_points, out_dev, stream);
-    return launch_folded_net(h->net, q, stream);
+    if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
+    return mlp_run(h, xyz_dev, n_queries, n_points, out_dev, use_tc ? NPHM_IMPL_TC : NPHM_IMPL_SIMT, stream);
 }

@@ -54,6 +54,25 @@ def nabla(decoder_shape, xc, cond, anchors):
     return sdf_pred, gradient(sdf_pred, xc)
 
 
+def _fused_search_condition(decoder_expr, xc, cond, anchors):
+    """Per-query condition rows (B x C) when the device-side Broyden search applies: a `DeformationNetwork` in eval mode
+    on CUDA whose condition is constant per query (modes compress / expr_only / glob_only), else None."""
+    from .deepSDF import DeformationNetwork
+    from .. import _native
+    if not isinstance(decoder_expr, DeformationNetwork) or decoder_expr.training:
+        return None
+    if decoder_expr.mode not in ('compress', 'expr_only', 'glob_only') or not xc.is_cuda:
+        return None
+    with torch.no_grad():
+        if not decoder_expr.defDeepSDF._fused_ok(xc.detach(), cond.detach()):
+            return None
+        lat = _native.constant_latent_rows(cond.detach())
+        if lat is None:
+            return None
+        return decoder_expr._condition(xc.detach(), lat.unsqueeze(1), anchors.detach() if anchors is not None else None,
+                                       per_point=False)[:, 0].contiguous()
+
+
 def search(obs, cond, decoder_expr, anchors, multi_corresp=True):
     """Canonical correspondences of observed (posed) points: roots of x + F_ex(x) - obs.
     obs: B x N x 3.  Returns (xc_opt, result dict with 'valid_ids')."""
@@ -81,8 +100,16 @@ def search(obs, cond, decoder_expr, anchors, multi_corresp=True):
         err = (off + pts) - obs
         return err.flatten(0, 1)[mask].unsqueeze(-1)
 
+    fused_cond = _fused_search_condition(decoder_expr, xc_init.reshape(n_batch, -1, 3), cond, anchors)
     with torch.no_grad():
-        result = broyden(residual, xc_init, J_inv_init, cvg_thresh=1e-6, dvg_thresh=0.2, max_steps=15)
+        if fused_cond is not None:
+            # whole iteration on the device: one fused-MLP launch + one 3x3 update kernel per step (nphm_mlp_broyden_search)
+            x, diff, valid, _ = decoder_expr.defDeepSDF.engine().broyden_search(
+                obs, fused_cond, xc_init.reshape(n_batch, -1, 3), J_inv_init.reshape(n_batch, -1, 3, 3),
+                max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2)
+            result = {'result': x.reshape(-1, 3, 1), 'diff': diff.reshape(-1), 'valid_ids': valid.reshape(-1)}
+        else:
+            result = broyden(residual, xc_init, J_inv_init, cvg_thresh=1e-6, dvg_thresh=0.2, max_steps=15)
 
     if multi_corresp:
         xc_opt = result['result'].reshape(n_batch, n_point, -1, 3)

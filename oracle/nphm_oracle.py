@@ -217,6 +217,46 @@ def deformation_forward(state_dict, xyz, z_id, z_ex, anchors) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------------------
+# Broyden correspondence search (iterative_root_finding.py:5-71 `broyden`, residual of `search` :142-147)
+# --------------------------------------------------------------------------------------------------
+def broyden_search(field, obs, x_init, J_inv_init, max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2, eps=1e-6):
+    """Roots of ``x + field(x) - obs`` per row.  ``field``: (N,3) -> (N,3) fp32 (rows independent); obs, x_init (N,3);
+    J_inv_init (N,3,3).  Returns (x, diff, valid): like the reference, ``x`` is where each sample stopped (its `x_opt`
+    aliases `x`, :34), ``diff`` the smallest residual norm seen, ``valid = diff < cvg_thresh``."""
+    obs = np.asarray(obs, F32)
+    x = np.array(x_init, F32)
+    J = np.array(J_inv_init, F32)
+    gx = ((field(x) + x) - obs).astype(F32)
+    upd = -np.einsum('nij,nj->ni', J, gx).astype(F32)
+    best = np.sqrt((gx * gx).sum(-1)).astype(F32)
+    act = np.ones(x.shape[0], bool)
+    for _ in range(max_steps):
+        dx = upd                                                      # rows of the currently active samples
+        x[act] = x[act] + dx
+        gnew = ((field(x) + x) - obs).astype(F32)[act]
+        dg = (gnew - gx[act]).astype(F32)
+        gx[act] = gx[act] + dg
+        nrm = np.sqrt((gx * gx).sum(-1)).astype(F32)
+        better = nrm < best
+        best[better] = nrm[better]
+        new_act = (best > cvg_thresh) & (nrm < dvg_thresh)
+        if not new_act.any():
+            break
+        sel = new_act[act]                                            # active sets are nested
+        dx, dg = dx[sel], dg[sel]
+        Ja = J[new_act]
+        vT = np.einsum('ni,nij->nj', dx, Ja).astype(F32)
+        a = (dx - np.einsum('nij,nj->ni', Ja, dg)).astype(F32)
+        b = (vT * dg).sum(-1).astype(F32)
+        b = np.where(b >= 0, b + F32(eps), b - F32(eps)).astype(F32)
+        Ja = (Ja + (a / b[:, None])[:, :, None] * vT[:, None, :]).astype(F32)
+        J[new_act] = Ja
+        upd = -np.einsum('nij,nj->ni', Ja, gx[new_act]).astype(F32)
+        act = new_act
+    return x, best, best < cvg_thresh
+
+
+# --------------------------------------------------------------------------------------------------
 # Adam (fitting.py:35, torch.optim.Adam defaults, torch 2.11 single-tensor update order)
 # --------------------------------------------------------------------------------------------------
 def adam_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):

@@ -101,3 +101,54 @@ def test_joint_fitter_on_gpu_follows_reference(cuda_device):
           % (100 * ci, 100 * ce))
     assert ci > 0.9 and ce > 0.9
     assert np.abs(anchors.detach().cpu().numpy()[0] - g['anchors_final']).max() < 2e-3
+
+
+def test_device_broyden_search_matches_reference_and_oracle(cuda_device):
+    """nphm_mlp_broyden_search (through `search`) against the reference's run (search.npz), the numpy oracle and the
+    Python-loop mirror of `broyden` on the same inputs.  Root accuracy: the iteration stops at |residual| < 1e-6, so two
+    runs agree to a few 1e-6 times |J^-1|; 5e-5 abs on the correspondences, >= 97 % identical valid flags."""
+    from test_oracle import _search_setup
+    from nphm_b200.models import iterative_root_finding as irf
+    g, dfn, obs, cond, anchors = _search_setup(cuda_device)
+    n = obs.shape[1]
+    xc, res = irf.search(obs, cond.repeat(1, n, 1), dfn, anchors, multi_corresp=False)
+    assert res['result'].shape == (2 * n, 3, 1) and res['valid_ids'].shape == (2, n) and res['valid_ids'].dtype == torch.bool
+    xc_np, valid, diff = xc.cpu().numpy(), res['valid_ids'].cpu().numpy(), res['diff'].cpu().numpy().reshape(2, n)
+    both = valid & g['valid']
+    assert (valid == g['valid']).mean() >= 0.97
+    assert np.abs(xc_np[both] - g['xc'][both]).max() < 5e-5
+    assert (diff[valid] < 1e-6).all() and (diff[~valid] >= 1e-6).all()
+    # roots really are roots: x + F(x) = obs on the converged samples (checked with the fp32 FFMA kernel)
+    with torch.no_grad():
+        off, _ = dfn(xc, cond.repeat(1, n, 1), anchors)
+    resid = (off + xc - obs).norm(dim=-1).cpu().numpy()
+    assert resid[valid].max() < 5e-6
+    # the Python-loop mirror (same network kernel, torch 3x3 algebra) on the same inputs
+    saved = irf._fused_search_condition
+    irf._fused_search_condition = lambda *a, **k: None
+    try:
+        xc_py, res_py = irf.search(obs, cond.repeat(1, n, 1), dfn, anchors, multi_corresp=False)
+    finally:
+        irf._fused_search_condition = saved
+    vpy = res_py['valid_ids'].cpu().numpy()
+    assert (valid == vpy).mean() >= 0.97
+    assert np.abs(xc_np[valid & vpy] - xc_py.detach().cpu().numpy()[valid & vpy]).max() < 5e-5
+
+
+def test_device_broyden_search_edge_cases(cuda_device):
+    """max_steps = 0 returns the start point with its residual; an exact start is valid immediately; empty input."""
+    from conftest import make_deformation
+    dfn = make_deformation(cuda_device)
+    eng = dfn.defDeepSDF.engine()
+    torch.manual_seed(3)
+    cond = torch.randn(1, 232, device=cuda_device) * 0.1
+    x0 = torch.randn(1, 70, 3, device=cuda_device) * 0.2
+    obs = x0 + eng.query(x0, cond)                                  # x0 is an exact root
+    eye = torch.eye(3, device=cuda_device).expand(1, 70, 3, 3).contiguous()
+    x, diff, valid, steps = eng.broyden_search(obs, cond, x0, eye)
+    assert valid.all() and steps <= 3 and torch.equal(x, x0)
+    x, diff, valid, steps = eng.broyden_search(obs + 0.05, cond, x0, eye, max_steps=0)
+    assert steps == 0 and torch.equal(x, x0) and not valid.any()
+    assert torch.allclose(diff, torch.full_like(diff, 0.05 * 3 ** 0.5), atol=1e-5)
+    x, diff, valid, steps = eng.broyden_search(obs[:, :0], cond, x0[:, :0], eye[:, :0])
+    assert x.shape == (1, 0, 3) and valid.numel() == 0

@@ -120,3 +120,39 @@ def test_mc_oracle_mesh_from_logits_negates_in_place():
     verts, tris = O.mesh_from_logits(flat, [-.55, -.5, -.95], [0.55, 0.75, 0.4], 12)
     assert np.array_equal(flat, -keep)
     assert verts[:, 0].min() >= -.55 and verts[:, 2].max() <= 0.4 and len(tris) > 0
+
+
+def _search_setup(device='cpu'):
+    """Deformation field, condition tensors and initial inverse Jacobians of tests/golden/search.npz."""
+    import torch
+    from nphm_b200.models.diff_operators import jac
+    g = load_golden('search.npz')
+    dfn = make_deformation(device)
+    with torch.no_grad():
+        dfn.defDeepSDF.lin6.weight.mul_(float(g['out_scale']))
+        dfn.defDeepSDF.lin6.bias.mul_(float(g['out_scale']))
+    obs = torch.from_numpy(g['obs']).to(device)
+    nb, n, _ = obs.shape
+    cond = torch.cat([torch.from_numpy(g['latent_id']).reshape(1, 1, -1).repeat(nb, 1, 1),
+                      torch.from_numpy(g['z_ex']).unsqueeze(1)], dim=-1).to(device)
+    anchors = torch.from_numpy(g['anchors']).to(device).reshape(1, 1, 39, 3).repeat(nb, n, 1, 1)
+    return g, dfn, obs, cond, anchors
+
+
+def test_oracle_broyden_search_against_reference():
+    """numpy restatement of `broyden` + the residual of `search` vs the reference's own run (search.npz)."""
+    import torch
+    from nphm_b200.models.diff_operators import jac
+    g, dfn, obs, cond, anchors = _search_setup()
+    n = obs.shape[1]
+    J_inv = jac(dfn, obs.clone(), cond.repeat(1, n, 1), anchors).inverse().detach().numpy()
+    sd = sd_numpy(dfn)
+    agree = 0
+    for q in range(obs.shape[0]):
+        field = lambda x, q=q: O.deformation_forward(sd, x, g['latent_id'], g['z_ex'][q], g['anchors'])
+        x, diff, valid = O.broyden_search(field, g['obs'][q], g['obs'][q], J_inv[q])
+        both = valid & g['valid'][q]
+        agree += int((valid == g['valid'][q]).sum())
+        assert np.abs(x[both] - g['xc'][q][both]).max() < 5e-5
+        assert (diff[valid] < 1e-6).all()
+    assert agree >= 0.97 * g['valid'].size, agree
