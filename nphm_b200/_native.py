@@ -113,10 +113,8 @@ def lib() -> ctypes.CDLL:
     L.nphm_mlp_broyden_search.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
                                           c_float, c_float, c_float, c_void_p, c_void_p, POINTER(c_int), c_void_p,
                                           c_void_p]
-    for name in EXPORTED_SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is c_int and name not in ('nphm_abi_version',):
-            pass
+    for name in EXPORTED_SYMBOLS:                      # fail at load time, not at first use, if a symbol is missing
+        getattr(L, name)
     _lib = L
     return L
 

@@ -456,12 +456,8 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
         SimtQuery q{};
         q.xyz = points_dev; q.first = 0; q.total = n_points; q.n_points = n_points; q.n_queries = 1; q.quirk_period = 0;
         q.cvec = h->cvec.as<float>(); q.anchors = h->anchors.as<float>(); q.blend = 1;
-        q.out = b.out; q.members_out = b.member_s;
-        const bool saved_prune = h->tc_prune;
-        h->tc_prune = false;
-        rc = tc_ensemble_launch(h, q, stream);
-        h->tc_prune = saved_prune;
-        if (rc) return rc;
+        q.out = b.out; q.members_out = b.member_s; q.exact = 1;
+        if ((rc = tc_ensemble_launch(h, q, stream))) return rc;
     } else {
         fit::fit_member_kernel<false><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
         NPHM_CUDA_CHECK(cudaGetLastError());
