@@ -41,9 +41,20 @@ constexpr int kSlabBytes = kNP2 * 64;
 constexpr int kGroupBytes = 7 * kSlabBytes;             // weight groups: L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
 constexpr int kL1Bytes = kKS1 * kSlab1Bytes, kL2Bytes = kKS2 * kSlabBytes, kL3Bytes = kKS3 * kSlabBytes;
 constexpr int kSetBytes = kL1Bytes + kL2Bytes + kL3Bytes;     // 359424 per weight set
-constexpr int kColD = 0, kColAhi = 208, kColAlo = 312;
-// spare columns: first 96 K values (hi | lo) of layer 1's A operand, written ahead of time for the NEXT member
+constexpr int kColD = 0, kColAhi = 208, kColAlo = 312;      // map of the MMA self-test / micro-benchmark kernels only
+// TMEM column map of the ensemble kernel.  Operands rotate through the 512 columns so that (a) the layer-2 MMAs can run
+// WHILE the layer-1 epilogue is still producing their A operand (D2 is disjoint from D1 and A1) and (b) the first six
+// k-steps of the next member's layer 1 can be issued while its remaining layer-0 outputs are still being computed:
+//   A0a (layer-1 A, K 0..95, written one member ahead)   hi [416,464) lo [464,512)
+//   A0b (layer-1 A, K 96..207)                            hi [0,56)    lo [56,112)
+//   D1 [112,224)   A1 (layer-2 A, K 0..111) hi [0,56) lo [56,112)   D2 [304,512)
+//   A2 (layer-3 A, K 0..207) hi [0,104) lo [104,208)      D3 [208,416)
+// Every overlap is between objects whose lifetimes are separated by an mbarrier (see the hazard notes in the kernel).
 constexpr int kColSpareHi = 416, kColSpareLo = 464, kNA = 96;
+constexpr int kColA0bHi = 0, kColA0bLo = 56;
+constexpr int kColD1 = 112, kColA1Hi = 0, kColA1Lo = 56;
+constexpr int kColD2 = 304, kColA2Hi = 0, kColA2Lo = 104;
+constexpr int kColD3 = 208;
 constexpr int kRecSlots = 3;
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
@@ -63,7 +74,7 @@ struct __align__(128) Smem {
     float partial[kParts - 1][128];
     uint64_t w_full[2], w_empty[2];
     uint64_t rec_full[kRecSlots], rec_empty[kRecSlots];
-    uint64_t a_ready, d_ready, mask_ready;
+    uint64_t a0a_ready, a0b_ready, a1_ready[3], a2_ready, d_ready, mask_ready;
     unsigned long long maskq[2][4];
     uint32_t tmem_base;
 };
@@ -87,36 +98,37 @@ struct Params {
     int blocked, px0, px1, by, bz;
 };
 
-// store 8 consecutive activations (next-layer K indices k0..k0+7) as fp16 hi/lo pairs
-__device__ __forceinline__ void store_a8(uint32_t tmem_lane_base, int k0, const float (&v)[8])
+// store 8 consecutive activations as fp16 hi/lo pairs: col_hi / col_lo = TMEM column of the first pair (2 K values per column)
+__device__ __forceinline__ void store_a8(uint32_t col_hi, uint32_t col_lo, const float (&v)[8])
 {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    tc_st4(tmem_lane_base + kColAhi + (k0 >> 1), hi);
-    tc_st4(tmem_lane_base + kColAlo + (k0 >> 1), lo);
+    tc_st4(col_hi, hi);
+    tc_st4(col_lo, lo);
 }
-__device__ __forceinline__ void store_a4(uint32_t tmem_lane_base, int k0, const float (&v)[4])
+__device__ __forceinline__ void store_a4(uint32_t col_hi, uint32_t col_lo, const float (&v)[4])
 {
     uint32_t h0, l0, h1, l1;
     split2(v[0], v[1], h0, l0); split2(v[2], v[3], h1, l1);
-    tc_st2(tmem_lane_base + kColAhi + (k0 >> 1), h0, h1);
-    tc_st2(tmem_lane_base + kColAlo + (k0 >> 1), l0, l1);
+    tc_st2(col_hi, h0, h1);
+    tc_st2(col_lo, l0, l1);
 }
-__device__ __forceinline__ void init_d4(uint32_t tmem_lane_base, int col, const float *bias)
+// accumulator columns + per-column constant (bias / folded latent part) from the shared-memory record
+__device__ __forceinline__ void add_bias8(uint32_t (&r)[8], const float *bias)
 {
-    const float4 b0 = *reinterpret_cast<const float4 *>(bias + col);
-    const uint32_t r[4] = {__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w)};
-    tc_st4(tmem_lane_base + kColD + col, r);
+    const float4 b0 = *reinterpret_cast<const float4 *>(bias);
+    const float4 b1 = *reinterpret_cast<const float4 *>(bias + 4);
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + b[e]);
 }
-// preload 8 accumulator columns with a bias vector from shared memory
-__device__ __forceinline__ void init_d8(uint32_t tmem_lane_base, int col, const float *bias)
+__device__ __forceinline__ void add_bias4(uint32_t (&r)[4], const float *bias)
 {
-    const float4 b0 = *reinterpret_cast<const float4 *>(bias + col);
-    const float4 b1 = *reinterpret_cast<const float4 *>(bias + col + 4);
-    const uint32_t r[8] = {__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w),
-                           __float_as_uint(b1.x), __float_as_uint(b1.y), __float_as_uint(b1.z), __float_as_uint(b1.w)};
-    tc_st8(tmem_lane_base + kColD + col, r);
+    const float4 b0 = *reinterpret_cast<const float4 *>(bias);
+    const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + b[e]);
 }
 
 template <bool PRUNE>
@@ -131,7 +143,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
         for (int i = 0; i < kRecSlots; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps); }
-        mbar_init(&sm.a_ready, kEpiWarps);
+        mbar_init(&sm.a0a_ready, kEpiWarps);
+        mbar_init(&sm.a0b_ready, kEpiWarps);
+        for (int i = 0; i < 3; ++i) mbar_init(&sm.a1_ready[i], kEpiWarps);
+        mbar_init(&sm.a2_ready, kEpiWarps);
         mbar_init(&sm.d_ready, 1);
         mbar_init(&sm.mask_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         // =========================================================================== MMA issuer
         if (lane == 0) {
             int wb = 0;
-            uint32_t wph = 0, a_ph = 0, tcount = 0;
+            uint32_t wph = 0, mph = 0, tcount = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 unsigned long long mask = (1ull << p.n_members) - 1;
                 if (PRUNE) {
@@ -197,36 +212,82 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 }
                 for (int m = 0; m < p.n_members; ++m) {
                     if (PRUNE && !((mask >> m) & 1)) continue;
-#pragma unroll 1
-                    for (int g = 0; g < 4; ++g) {
-                        // group -> (layer shape, k-step range): L1 | L2 | L3 k-steps 0-6 | L3 k-steps 7-12
-                        const int n = g == 0 ? kNP1 : kNP2;
-                        const int ks = g == 0 ? kKS1 : (g == 3 ? 6 : 7);
-                        const int k0 = g == 3 ? 7 : 0;
-                        const uint32_t idesc = make_idesc(n);
-                        if (g != 3) {
-                            mbar_wait(&sm.a_ready, a_ph);
-                            a_ph ^= 1;
-                        }
+                    // one k-step = 3 MMAs (hi*hi + hi*lo + lo*hi); `fresh` overwrites the accumulator (no bias preload)
+                    auto kstep = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t slab, int n, uint32_t idesc, bool fresh) {
+                        const uint64_t b_hi = make_desc(slab, 128, 256);
+                        const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
+                        tc_mma_ts(d, a_hi, b_hi, idesc, fresh ? 0 : 1);
+                        tc_mma_ts(d, a_hi, b_lo, idesc, 1);
+                        tc_mma_ts(d, a_lo, b_hi, idesc, 1);
+                    };
+                    auto next_buf = [&]() { if (++wb == 2) { wb = 0; wph ^= 1; } };
+                    // ---- layer 1 (N 112): k-steps 0-5 read the operand written one member ahead, 6-12 the rest of layer 0
+                    {
+                        const uint32_t idesc = make_idesc(kNP1);
+                        mbar_wait(&sm.a0a_ready, mph);
                         mbar_wait(&sm.w_full[wb], wph);
                         tc_fence_after();
                         const uint32_t base = smem_u32(sm.wbuf[wb]);
 #pragma unroll 1
-                        for (int j = 0; j < ks; ++j) {
-                            const uint32_t slab = base + j * n * 64;
-                            const uint64_t b_hi = make_desc(slab, 128, 256);
-                            const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
-                            const bool spare = g == 0 && j < kNA / 16;
-                            const uint32_t a_hi = tmem + (spare ? kColSpareHi : kColAhi) + (k0 + j) * 8;
-                            const uint32_t a_lo = tmem + (spare ? kColSpareLo : kColAlo) + (k0 + j) * 8;
-                            tc_mma_ts(tmem + kColD, a_hi, b_hi, idesc, 1);
-                            tc_mma_ts(tmem + kColD, a_hi, b_lo, idesc, 1);
-                            tc_mma_ts(tmem + kColD, a_lo, b_hi, idesc, 1);
+                        for (int j = 0; j < kNA / 16; ++j)
+                            kstep(tmem + kColD1, tmem + kColSpareHi + j * 8, tmem + kColSpareLo + j * 8, base + j * kSlab1Bytes,
+                                  kNP1, idesc, j == 0);
+                        mbar_wait(&sm.a0b_ready, mph);
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int j = kNA / 16; j < kKS1; ++j)
+                            kstep(tmem + kColD1, tmem + kColA0bHi + (j - kNA / 16) * 8, tmem + kColA0bLo + (j - kNA / 16) * 8,
+                                  base + j * kSlab1Bytes, kNP1, idesc, false);
+                        tc_commit(&sm.w_empty[wb]);
+                        tc_commit(&sm.d_ready);
+                        next_buf();
+                    }
+                    // ---- layer 2 (N 208, K 112): issued group by group while the layer-1 epilogue produces its A operand
+                    {
+                        const uint32_t idesc = make_idesc(kNP2);
+                        mbar_wait(&sm.w_full[wb], wph);
+                        const uint32_t base = smem_u32(sm.wbuf[wb]);
+                        bool fresh = true;
+#pragma unroll 1
+                        for (int grp = 0; grp < 3; ++grp) {
+                            const int j0 = grp == 0 ? 4 : (grp == 1 ? 2 : 0), j1 = grp == 0 ? 7 : (grp == 1 ? 4 : 2);
+                            mbar_wait(&sm.a1_ready[grp], mph);
+                            tc_fence_after();
+                            for (int j = j0; j < j1; ++j) {
+                                kstep(tmem + kColD2, tmem + kColA1Hi + j * 8, tmem + kColA1Lo + j * 8, base + j * kSlabBytes, kNP2,
+                                      idesc, fresh);
+                                fresh = false;
+                            }
                         }
                         tc_commit(&sm.w_empty[wb]);
-                        if (g != 2) tc_commit(&sm.d_ready);
-                        if (++wb == 2) { wb = 0; wph ^= 1; }
+                        tc_commit(&sm.d_ready);
+                        next_buf();
                     }
+                    // ---- layer 3 (N 208, K 208) in two weight groups
+                    {
+                        const uint32_t idesc = make_idesc(kNP3);
+                        mbar_wait(&sm.a2_ready, mph);
+                        mbar_wait(&sm.w_full[wb], wph);
+                        tc_fence_after();
+                        uint32_t base = smem_u32(sm.wbuf[wb]);
+#pragma unroll 1
+                        for (int j = 0; j < 7; ++j)
+                            kstep(tmem + kColD3, tmem + kColA2Hi + j * 8, tmem + kColA2Lo + j * 8, base + j * kSlabBytes, kNP3, idesc,
+                                  j == 0);
+                        tc_commit(&sm.w_empty[wb]);
+                        next_buf();
+                        mbar_wait(&sm.w_full[wb], wph);
+                        tc_fence_after();
+                        base = smem_u32(sm.wbuf[wb]);
+#pragma unroll 1
+                        for (int j = 7; j < kKS3; ++j)
+                            kstep(tmem + kColD3, tmem + kColA2Hi + j * 8, tmem + kColA2Lo + j * 8, base + (j - 7) * kSlabBytes, kNP3,
+                                  idesc, false);
+                        tc_commit(&sm.w_empty[wb]);
+                        tc_commit(&sm.d_ready);
+                        next_buf();
+                    }
+                    mph ^= 1;
                 }
             }
         }
@@ -236,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
         const int q = warp & 3, part = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
-        uint32_t d_ph = 0, tcount = 0, rcount = 0;
+        uint32_t d_ph = 0, m_ph = 0, tcount = 0, rcount = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             int qi;
             long long idx, g;
@@ -349,14 +410,27 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
 
                 // Column ownership (balanced: 6.5 chunks per warp and layer): 8-column chunks c = part + 4i (i < 6)
                 // cover columns 0..191, the 4-column piece 192 + 4*part covers 192..207; for the 112-column layer 1:
-                // chunks part + 4i (i < 3) and the piece 96 + 4*part.  A column is always read, converted and
-                // re-initialised by the same thread (stages with different ownership are separated by the quarter barrier).
+                // chunks part + 4i (i < 3) and the piece 96 + 4*part.
+                // Hazard notes (TMEM regions are reused, see the column map): a region is only overwritten after an
+                // mbarrier has proven that its previous readers are done -
+                //   A0b/A1 [0,112)  <- previous readers are MMAs that completed before the d_ready this warp waited on;
+                //   D1 [112,224)    <- overlaps D3: the issuer waits for a0a_ready, which a warp signals after its last D3 read;
+                //   D2 [304,512)    <- overlaps D3 and the A0a columns: both dead once layer 1 of this member was issued;
+                //   A2 [0,208)      <- D1/A1 readers finished before d_ready (layer 2) fired;
+                //   A0a [416,512)   <- overlaps D2: written only after a2_ready COMPLETED (every warp finished reading D2).
                 const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
+                auto publish = [&](uint64_t *bar) {          // my TMEM stores are visible to the MMA issuer after this
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar);
+                };
 
-                // ---------------- layer 0 on CUDA cores -> A operand of layer 1; D preloaded with S*b1
-                if (!a_done) layer0_a(rec, cx, cy, cz);
-#pragma unroll 1
-                for (int c = part; c < 12; c += kParts) init_d8(tl, c * 8, rec + kRecB1);
+                // ---------------- layer 0 on CUDA cores -> A operand of layer 1
+                if (!a_done) {
+                    layer0_a(rec, cx, cy, cz);
+                    publish(&sm.a0a_ready);
+                }
 #pragma unroll 1
                 for (int c = 12 + part; c < 24; c += kParts) {
                     const int n0 = c * 8;
@@ -367,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
-                    store_a8(tl, n0, v);
+                    store_a8(tl + kColA0bHi + ((n0 - kNA) >> 1), tl + kColA0bLo + ((n0 - kNA) >> 1), v);
                 }
                 {
                     const int n0 = 192 + 4 * part;               // rows >= 200 are zero: sp(0) meets zero weights
@@ -378,50 +452,42 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
-                    store_a4(tl, n0, v);
-                    init_d4(tl, 96 + 4 * part, rec + kRecB1);
+                    store_a4(tl + kColA0bHi + ((n0 - kNA) >> 1), tl + kColA0bLo + ((n0 - kNA) >> 1), v);
                 }
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.a_ready);
+                publish(&sm.a0b_ready);
 
-                // ---------------- epilogue of layer 1 (N = 101 -> K of layer 2 = [h1, c, 0...]); D <- S*v2
+                // ---------------- epilogue of layer 1 (N = 101 -> K of layer 2 = [h1, c, 0...]), published in three groups
+                // (k-steps 4-6 | 2-3 | 0-1) so that the layer-2 MMAs start while the rest is still being converted
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = part; c < 12; c += kParts) {
-                    const int n0 = c * 8;
-                    uint32_t r[8];
-                    tc_ld8(tl + kColD + n0, r);
-                    tc_wait_ld();
-                    float v[8];
-                    sp8(r, v);
-                    store_a8(tl, n0, v);
-                    init_d8(tl, n0, rec + kRecB2);
-                }
                 {
                     const int n0 = 96 + 4 * part;                // 96..99 | 100, c | padding | padding
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
                     if (part < 2) {
                         uint32_t r[4];
-                        tc_ld4(tl + kColD + n0, r);
+                        tc_ld4(tl + kColD1 + n0, r);
                         tc_wait_ld();
+                        add_bias4(r, rec + kRecB1 + n0);
                         if (part == 0) sp4(r, v);
                         else { v[0] = sp_t(__uint_as_float(r[0])); v[1] = cx; v[2] = cy; v[3] = cz; }
                     }
-                    store_a4(tl, n0, v);
-                    init_d4(tl, n0, rec + kRecB2);
+                    store_a4(tl + kColA1Hi + (n0 >> 1), tl + kColA1Lo + (n0 >> 1), v);
                 }
 #pragma unroll 1
-                for (int c = 14 + part; c < 26; c += kParts) init_d8(tl, c * 8, rec + kRecB2);   // columns 112..207
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.a_ready);
+                for (int grp = 0; grp < 3; ++grp) {
+                    const int n0 = (8 - 4 * grp + part) * 8;     // chunk 8+part, 4+part, part
+                    uint32_t r[8];
+                    tc_ld8(tl + kColD1 + n0, r);
+                    tc_wait_ld();
+                    add_bias8(r, rec + kRecB1 + n0);
+                    float v[8];
+                    sp8(r, v);
+                    store_a8(tl + kColA1Hi + (n0 >> 1), tl + kColA1Lo + (n0 >> 1), v);
+                    publish(&sm.a1_ready[grp]);
+                }
 
-                // ---------------- epilogue of layer 2; D <- S*b3
+                // ---------------- epilogue of layer 2
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
@@ -429,27 +495,24 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 for (int c = part; c < 24; c += kParts) {
                     const int n0 = c * 8;
                     uint32_t r[8];
-                    tc_ld8(tl + kColD + n0, r);
+                    tc_ld8(tl + kColD2 + n0, r);
                     tc_wait_ld();
+                    add_bias8(r, rec + kRecB2 + n0);
                     float v[8];
                     sp8(r, v);
-                    store_a8(tl, n0, v);
-                    init_d8(tl, n0, rec + kRecB3);
+                    store_a8(tl + kColA2Hi + (n0 >> 1), tl + kColA2Lo + (n0 >> 1), v);
                 }
                 {
                     const int n0 = 192 + 4 * part;
                     uint32_t r[4];
-                    tc_ld4(tl + kColD + n0, r);
+                    tc_ld4(tl + kColD2 + n0, r);
                     tc_wait_ld();
+                    add_bias4(r, rec + kRecB2 + n0);
                     float v[4];
                     sp4(r, v);
-                    store_a4(tl, n0, v);
-                    init_d4(tl, n0, rec + kRecB3);
+                    store_a4(tl + kColA2Hi + (n0 >> 1), tl + kColA2Lo + (n0 >> 1), v);
                 }
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.a_ready);
+                publish(&sm.a2_ready);
 
                 // ---------------- in the shadow of the layer-3 MMAs: first part of layer 0 of the next member of this tile
                 {
@@ -461,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         const float *nrec = sm.rec[nslot];
                         float nx, ny, nz;
                         member_coords(nrec, nx, ny, nz);
+                        mbar_wait(&sm.a2_ready, m_ph);           // the A0a columns overlap D2: every warp must be done reading it
                         layer0_a(nrec, nx, ny, nz);
                     }
                 }
@@ -474,8 +538,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 for (int c = part; c < 24; c += kParts) {
                     const int n0 = c * 8;
                     uint32_t r[8];
-                    tc_ld8(tl + kColD + n0, r);
+                    tc_ld8(tl + kColD3 + n0, r);
                     tc_wait_ld();
+                    add_bias8(r, rec + kRecB3 + n0);
                     const float4 w0 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0);
                     const float4 w1 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0 + 4);
                     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -487,8 +552,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 {
                     const int n0 = 192 + 4 * part;
                     uint32_t r[4];
-                    tc_ld4(tl + kColD + n0, r);
+                    tc_ld4(tl + kColD3 + n0, r);
                     tc_wait_ld();
+                    add_bias4(r, rec + kRecB3 + n0);
                     const float4 w0 = *reinterpret_cast<const float4 *>(rec + kRecW4 + n0);
                     const float w[4] = {w0.x, w0.y, w0.z, w0.w};
                     float v[4];
@@ -496,6 +562,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc = fmaf(v[e], w[e], acc);
                 }
+                // next member's first layer-1 k-steps may go: its A0a is written and this warp no longer reads D3 (= D1's columns)
+                if (a_done) publish(&sm.a0a_ready);
+                m_ph ^= 1;
                 if (part != 0) sm.partial[part - 1][row] = acc;
                 tc_fence_before();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");   // the warps of this lane quarter
@@ -644,7 +713,7 @@ __global__ void __launch_bounds__(160, 1) mma_selftest_kernel(const float *__res
             float v[8];
             for (int e = 0; e < 8; ++e) v[e] = A[(size_t)row * ks * 16 + k0 + e];
             if (variant & 2) for (int e = 0; e < 8; e += 2) { const float t = v[e]; v[e] = v[e + 1]; v[e + 1] = t; }
-            store_a8(tl, k0, v);
+            store_a8(tl + kColAhi + (k0 >> 1), tl + kColAlo + (k0 >> 1), v);
         }
         const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < n; c += 8) tc_st8(tl + kColD + c, zero);
