@@ -120,11 +120,14 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
+        if os.environ.get('NPHM_BENCH_NO_SAMPLER'):
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', os.environ.get('NPHM_BENCH_SAMPLE_MS', '100')],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -134,6 +137,10 @@ class ClockSampler:
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
+
+    def mark(self):
+        """Start of the timed region: earlier samples (taken while nvidia-smi initialised, during warm-up) are dropped."""
+        self.first = len(self.lines)
 
     def stop(self):
         if self.proc is None:
@@ -145,7 +152,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -206,15 +213,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing --------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local)
+    n_warm = max(args.warmup, 3)
+    for i in range(n_warm):
+        if i == n_warm - 1:
+            sampler.start()             # nvidia-smi takes driver locks while it initialises: let that happen in warm-up
         step_device()
         flush.zero_()
     import gc
     gc.collect()
     gc.disable()                        # no collector pauses inside the timed regions (host sits between MC passes)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     launches['n'] = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
@@ -307,6 +317,16 @@ def main():
         if peak_tf is None:
             peak_tf, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
         achieved_tf = FLOP_PER_POINT * total / (sdf_ms * 1e-3) / 1e12
+        # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture of this workload
+        traffic, traffic_src = None, 'no ncu capture recorded for this resolution'
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                rec = json.load(f).get(str(res))
+            if rec:
+                traffic = rec['dram_bytes_read'] + rec['dram_bytes_write']
+                traffic_src = 'bytes, ' + rec['source'] + ' (profiles/traffic.json)'
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             'metric': 'sdf_query_points_per_s', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
@@ -322,9 +342,10 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'get_logits + mesh_from_logits (drop-in, numpy in/out)'},
             'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved_tf / peak_tf, 'traffic': None,
+                         'frac': achieved_tf / peak_tf, 'traffic': traffic,
                          'note': 'dominant kernel = fused ensemble SDF query; algorithmic 9.616 MFLOP/point (dense '
-                                 'reference formulation) / CUDA-event time of the query; peak: ' + peak_src},
+                                 'reference formulation) / CUDA-event time of the query; peak: ' + peak_src +
+                                 '; traffic: ' + traffic_src},
         }
         if pruned is not None:
             line['pruned_opt_in'] = pruned

@@ -18,7 +18,8 @@ import torch
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_PRUNED = 0, 1, 2, 3
 _IMPL_BY_NAME = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC, 'tc_pruned': IMPL_TC_PRUNED}
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libnphm_b200.so')
+# NPHM_B200_LIB: developer override used for A/B runs of kernel variants (tools/ab_bench.sh); default = the in-tree build
+_LIB_PATH = os.environ.get('NPHM_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libnphm_b200.so')
 _lib = None
 
 # every symbol include/nphm_b200.h declares (tests check that the library exports all of them)

@@ -9,7 +9,7 @@ namespace tc {
 constexpr float kS = 144.26950408889634f;            // 100 * log2(e)
 constexpr int kTmemCols = 512;
 #ifndef NPHM_POLY_MASK
-#define NPHM_POLY_MASK 0xAA          // which of 8 consecutive elements evaluate lg2(1+e) on the FMA pipe (bit set) vs MUFU
+#define NPHM_POLY_MASK 0x88          // which of 8 consecutive elements evaluate lg2(1+e) on the FMA pipe (bit set) vs MUFU
 #endif
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

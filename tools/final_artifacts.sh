@@ -12,7 +12,7 @@ timeout 300 python tools/bench_joint.py --steps 40 > gpurun_out/joint_$T.json 2>
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$T.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_$T.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ensemble_tc_kernel -c 1 -f -o gpurun_out/prof_tc_$T \
-    python bench.py --steps 1 --warmup 0 --res 128 --no-cpu-baseline > gpurun_out/prof_tc_$T.log 2>&1
+    python bench.py --steps 1 --warmup 0 --res 256 --no-cpu-baseline > gpurun_out/prof_tc_$T.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_fit_$T.csv \
     python tools/bench_fit.py --steps 4 > /dev/null 2>&1
 tail -3 gpurun_out/pytest_gpu_$T.log; cat gpurun_out/bench_$T.json; cat gpurun_out/bench_aux_$T.json gpurun_out/fit_$T.json gpurun_out/joint_$T.json

@@ -58,5 +58,23 @@ def kernel(path):
                         k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v))
 
 
+def traffic(path):
+    """DRAM bytes (read + write) of the captured launch as a JSON object, for bench.py's roofline.traffic."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    d = dict(zip(hdr, rows[2]))
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+
+    def val(k):
+        return float(d[k].replace(',', '')) * scale[units[hdr.index(k)]]
+    print(json.dumps({'kernel': d.get('Kernel Name'), 'dram_bytes_read': val('dram__bytes_read.sum'),
+                      'dram_bytes_write': val('dram__bytes_write.sum'),
+                      'gpu_time_ms': float(d['gpu__time_duration.sum'].replace(',', '')) *
+                      {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}[units[hdr.index('gpu__time_duration.sum')]],
+                      'source': 'ncu --set full --clock-control none, one launch of the bench workload'}))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'kernel': kernel, 'traffic': traffic}[sys.argv[1]](sys.argv[2])
