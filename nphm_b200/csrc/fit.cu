@@ -26,6 +26,7 @@ namespace fit {
 constexpr int TM = 2;
 constexpr int P = 32 * TM;
 constexpr int kThreads = 512;
+static_assert(TM == 2, "the activation hand-over copies float2 per lane");
 
 struct Dims {
     int n_members, n_symm, n_loc;
@@ -49,6 +50,7 @@ struct Buffers {
     const float *anchors;           // n_loc x 3
     const float *cvec;              // [members][cvec_stride]
     float *member_s;                // n x members
+    const float *acts;              // optional: hidden activations saved by the tensor-core forward, [member][tile128][feature][128]
     float *out, *S, *gsign;         // n each
     float *acc;                     // members x 2H   (sum delta0 | sum delta2)
     float *blend_acc;               // n_loc x 3
@@ -82,6 +84,26 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
     }
     float *rc = sm + (size_t)d.r_c * P, *rh0 = sm + (size_t)d.r_h0 * P, *rh1 = sm + (size_t)d.r_h1 * P;
     float *rh2 = sm + (size_t)d.r_h2 * P, *rh3 = sm + (size_t)d.r_h3 * P, *rs = sm + (size_t)d.r_s * P;
+    if (BWD && b.acts) {
+        // activations h0 | h1 | h2 | h3 were saved by the tensor-core forward pass: copy this tile's 64 columns of every
+        // feature row (256 contiguous bytes each) instead of recomputing the forward pass
+        const int n_feat = 3 * d.H + d.N1;
+        const long long tiles128 = (b.n + 127) / 128;
+        const float *src = b.acts + ((size_t)m * tiles128 + (blockIdx.x >> 1)) * n_feat * 128 + (blockIdx.x & 1) * P;
+        for (int f = warp; f < n_feat; f += nwarps) {
+            const int r = d.r_h0 + f + (f >= d.H + d.N1 ? 3 : 0);     // three skip-input rows sit between h1 and h2
+            const float2 v = *reinterpret_cast<const float2 *>(src + (size_t)f * 128 + lane * TM);
+            *reinterpret_cast<float2 *>(sm + (size_t)r * P + lane * TM) = v;
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const long long idx = p0 + lane * TM + i;
+                rs[lane * TM + i] = valid[i] ? b.member_s[idx * d.n_members + m] : 0.f;
+            }
+        }
+        __syncthreads();
+    } else {
     if (warp == 0) {
         float cx[TM], cy[TM], cz[TM];
 #pragma unroll
@@ -110,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
     __syncthreads();
     narrow_layer<TM>(L[4], L[4].Wt, cv + L[4].coff, rh3, rs, warp, lane, nwarps);
     __syncthreads();
+    }
 
     if (!BWD) {
         if (warp == 0) {
@@ -195,6 +218,187 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0 && s != 0.f) atomicAdd(acc + n, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward pass from the activations saved by the tensor-core forward (b.acts), on warp-level tensor-core MMAs.
+// One CTA per (64-point tile, member).  delta_{l-1} = (delta_l W_l) * sigma'(h_{l-1}) is a (64 x n_l) x (n_l x n_{l-1})
+// product: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small, big*big + big*small + small*big), which keeps
+// fp32-level accuracy (the latent gradient is pinned to the reference's autograd at 2e-4 of its max).  Shared-memory
+// rows use a pitch of 72 floats: fragment loads (4 rows x 8 points per instruction) then hit 32 distinct banks.
+constexpr int PP = 72;
+
+__device__ __forceinline__ void tf32_split(float x, uint32_t &big, uint32_t &small)
+{
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
+    const float r = x - __uint_as_float(big);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// rows_out[j][p] <- scale * sigma'(rows_out[j][p]) * sum_n delta[n][p] * W[n*ldw + j]      (j < J, n < K, 64 points)
+__device__ __forceinline__ void mma_layer_bwd(const float *__restrict__ W, int ldw, int K, int J, float scale,
+                                              const float *delta, float *rows_out, int warp, int lane, int nwarps)
+{
+    const int g = lane >> 2, t = lane & 3;
+    const int n_tiles = (J + 7) / 8, k_steps = (K + 7) / 8;
+    for (int nt0 = warp; nt0 < n_tiles; nt0 += 2 * nwarps) {
+        const int nt1 = nt0 + nwarps;                       // second column tile of this warp (may not exist)
+        const bool two = nt1 < n_tiles;
+        float c[2][4][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[u][mt][e] = 0.f;
+        const int j0 = nt0 * 8 + g, j1 = nt1 * 8 + g;
+#pragma unroll 2
+        for (int ks = 0; ks < k_steps; ++ks) {
+            const int ka = ks * 8 + t, kb = ka + 4;
+            uint32_t bb[2][2], bs[2][2];
+            {
+                const float w00 = (ka < K && j0 < J) ? __ldg(W + (size_t)ka * ldw + j0) : 0.f;
+                const float w01 = (kb < K && j0 < J) ? __ldg(W + (size_t)kb * ldw + j0) : 0.f;
+                tf32_split(w00, bb[0][0], bs[0][0]); tf32_split(w01, bb[0][1], bs[0][1]);
+                const float w10 = (two && ka < K && j1 < J) ? __ldg(W + (size_t)ka * ldw + j1) : 0.f;
+                const float w11 = (two && kb < K && j1 < J) ? __ldg(W + (size_t)kb * ldw + j1) : 0.f;
+                tf32_split(w10, bb[1][0], bs[1][0]); tf32_split(w11, bb[1][1], bs[1][1]);
+            }
+            const float *da = delta + (size_t)ka * PP, *db = delta + (size_t)kb * PP;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int p0 = mt * 16 + g;
+                const float a0 = ka < K ? da[p0] : 0.f, a1 = ka < K ? da[p0 + 8] : 0.f;
+                const float a2 = kb < K ? db[p0] : 0.f, a3 = kb < K ? db[p0 + 8] : 0.f;
+                uint32_t ab[4], as[4];
+                tf32_split(a0, ab[0], as[0]); tf32_split(a1, ab[1], as[1]);
+                tf32_split(a2, ab[2], as[2]); tf32_split(a3, ab[3], as[3]);
+                mma_tf32(c[0][mt], as, bb[0]); mma_tf32(c[0][mt], ab, bs[0]); mma_tf32(c[0][mt], ab, bb[0]);
+                if (two) { mma_tf32(c[1][mt], as, bb[1]); mma_tf32(c[1][mt], ab, bs[1]); mma_tf32(c[1][mt], ab, bb[1]); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const int jb = (u ? nt1 : nt0) * 8 + 2 * t;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb + (e & 1), pt = mt * 16 + g + ((e >> 1) << 3);
+                    if (j < J) {
+                        float *ptr = rows_out + (size_t)j * PP + pt;
+                        const float h = *ptr;
+                        const float sg = h > 0.2f ? 1.0f : -expm1f(-100.0f * h);
+                        *ptr = c[u][mt][e] * scale * sg;
+                    }
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dims d, const Weights w, const Buffers b,
+                                                                      float lambda_surface)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads / 32;
+    const int m = blockIdx.y;
+    const long long p0 = (long long)blockIdx.x * P;
+    const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
+    const bool has_anchor = m < d.n_loc;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (has_anchor) { ax = b.anchors[m * 3]; ay = b.anchors[m * 3 + 1]; az = b.anchors[m * 3 + 2]; }
+    // rows: h0 [0,H) | h1 [H, H+N1) | h2 | h3 | g_s (1 row)
+    float *rh0 = sm, *rh1 = rh0 + (size_t)d.H * PP, *rh2 = rh1 + (size_t)d.N1 * PP, *rh3 = rh2 + (size_t)d.H * PP;
+    float *rg = rh3 + (size_t)d.H * PP;
+    {
+        const int n_feat = 3 * d.H + d.N1;
+        const long long tiles128 = (b.n + 127) / 128;
+        const float *src = b.acts + ((size_t)m * tiles128 + (blockIdx.x >> 1)) * n_feat * 128 + (blockIdx.x & 1) * P;
+        for (int f = warp; f < n_feat; f += nwarps) {
+            const float2 v = *reinterpret_cast<const float2 *>(src + (size_t)f * 128 + lane * 2);
+            *reinterpret_cast<float2 *>(sm + (size_t)f * PP + lane * 2) = v;
+        }
+    }
+    // upstream gradient of this member's output per point, blend-path anchor gradient (same math as fit_member_kernel)
+    if (warp == 0) {
+        const float inv_count = 1.0f / b.stats[0];
+        float ba[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const long long idx = p0 + lane * 2 + i;
+            float gs = 0.f;
+            if (idx < b.n) {
+                const float x = b.points[idx * 3], y = b.points[idx * 3 + 1], z = b.points[idx * 3 + 2];
+                const float g_out = lambda_surface * b.gsign[idx] * inv_count;
+                const float Sp = b.S[idx] + 1e-6f;
+                float dd, r = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+                if (has_anchor) {
+                    dx = ax - x; dy = ay - y; dz = az - z;
+                    r = sqrtf(dx * dx + dy * dy + dz * dz);
+                    const float nrm = r + 10e-6f;
+                    dd = -(nrm * nrm);
+                } else {
+                    dd = -0.2f;
+                }
+                const float wk = expf(__fdiv_rn(dd, 0.01f));
+                gs = g_out * wk / Sp;
+                if (has_anchor && r > 0.f) {
+                    const float s_k = b.member_s[idx * d.n_members + m];
+                    const float g_w = g_out * (s_k - b.out[idx]) / Sp;
+                    const float coef = g_w * wk * (1.0f / 0.01f) * (-2.0f) * (r + 10e-6f) / r;
+                    ba[0] += coef * dx; ba[1] += coef * dy; ba[2] += coef * dz;
+                }
+            }
+            rg[lane * 2 + i] = gs;
+        }
+        if (has_anchor) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v = ba[a];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v != 0.f) atomicAdd(b.blend_acc + m * 3 + a, v);
+            }
+        }
+    }
+    __syncthreads();
+    // delta3 = g_s * w4 * sigma'(h3), in place over h3
+    {
+        const float *W4 = w.W[4] + (size_t)set * d.H;
+        const float2 gs = *reinterpret_cast<const float2 *>(rg + lane * 2);
+        for (int n = warp; n < d.H; n += nwarps) {
+            float2 *ptr = reinterpret_cast<float2 *>(rh3 + (size_t)n * PP + lane * 2);
+            const float2 h = *ptr;
+            const float w4 = __ldg(W4 + n);
+            float2 o;
+            o.x = gs.x * w4 * (h.x > 0.2f ? 1.0f : -expm1f(-100.0f * h.x));
+            o.y = gs.y * w4 * (h.y > 0.2f ? 1.0f : -expm1f(-100.0f * h.y));
+            *ptr = o;
+        }
+    }
+    __syncthreads();
+    mma_layer_bwd(w.W[3] + (size_t)set * d.H * d.H, d.H, d.H, d.H, 1.0f, rh3, rh2, warp, lane, nwarps);                    // delta2
+    __syncthreads();
+    mma_layer_bwd(w.W[2] + (size_t)set * d.H * d.H, d.H, d.H, d.N1, 0.70710678118654752f, rh2, rh1, warp, lane, nwarps);   // delta1
+    __syncthreads();
+    mma_layer_bwd(w.W[1] + (size_t)set * d.N1 * d.H, d.H, d.N1, d.H, 1.0f, rh1, rh0, warp, lane, nwarps);                   // delta0
+    __syncthreads();
+    float *acc = b.acc + (size_t)m * 2 * d.H;
+    for (int n = warp; n < 2 * d.H; n += nwarps) {
+        const float *row = (n < d.H ? rh0 + (size_t)n * PP : rh2 + (size_t)(n - d.H) * PP) + lane * 2;
+        const float2 v = *reinterpret_cast<const float2 *>(row);
+        float s2 = v.x + v.y;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (lane == 0 && s2 != 0.f) atomicAdd(acc + n, s2);
     }
 }
 
@@ -389,8 +593,10 @@ using namespace nphm;
 extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long n_points)
 {
     if (!h || n_points < 0) return -1;
-    const long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
-                             (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
+    long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
+                       (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
+    // hidden activations handed from the tensor-core forward to the backward kernel: [member][128-point tile][feature][128]
+    floats += (long long)h->n_members * ((n_points + 127) / 128) * (3 * h->cfg.hidden_dim + h->dims.N[1]) * 128;
     return floats * 4 + 1024;
 }
 
@@ -445,6 +651,9 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
     b.ganch = p; p += d.n_loc * 3;
     b.grad = p; p += d.lat_dim;
     NPHM_CUDA_CHECK(cudaMemsetAsync(zero_begin, 0, (size_t)(p - zero_begin) * sizeof(float), stream));
+    p += (4 - ((p - ws) & 3)) & 3;                                  // 16-byte alignment of the activation block
+    float *acts = p;
+    b.acts = nullptr;
 
     const int tiles = (int)ceil_div(n_points, fit::P);
     dim3 grid(tiles, h->n_members);
@@ -457,14 +666,23 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
         q.xyz = points_dev; q.first = 0; q.total = n_points; q.n_points = n_points; q.n_queries = 1; q.quirk_period = 0;
         q.cvec = h->cvec.as<float>(); q.anchors = h->anchors.as<float>(); q.blend = 1;
         q.out = b.out; q.members_out = b.member_s; q.exact = 1;
+        q.acts_out = acts;
         if ((rc = tc_ensemble_launch(h, q, stream))) return rc;
+        b.acts = acts;
     } else {
         fit::fit_member_kernel<false><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
         NPHM_CUDA_CHECK(cudaGetLastError());
     }
     fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
     NPHM_CUDA_CHECK(cudaGetLastError());
-    fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
+    if (b.acts) {
+        const size_t bsm = (size_t)(3 * d.H + d.N1 + 1) * fit::PP * sizeof(float);
+        NPHM_REQUIRE(bsm <= 227 * 1024, "nphm_fit_identity_step: hidden width %d too large for the backward kernel", d.H);
+        NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        fit::fit_backward_mma_kernel<<<grid, fit::kThreads, bsm, stream>>>(d, w, b, fp->lambda_surface);
+    } else {
+        fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
+    }
     NPHM_CUDA_CHECK(cudaGetLastError());
     fit::fit_member_grad_kernel<<<h->n_members, 128, 0, stream>>>(d, w, b);
     NPHM_CUDA_CHECK(cudaGetLastError());

@@ -56,6 +56,7 @@ constexpr int kColD1 = 112, kColA1Hi = 0, kColA1Lo = 56;
 constexpr int kColD2 = 304, kColA2Hi = 0, kColA2Lo = 104;
 constexpr int kColD3 = 208;
 constexpr int kRecSlots = 3;
+constexpr int kActFeat = kH + kN1 + kH + kH;      // features saved per point for the fitting backward: h0 | h1 | h2 | h3
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
 constexpr int kRecB1 = 832;        // 112
@@ -90,6 +91,7 @@ struct Params {
     long long quirk_period;
     float *out;
     float *members_out;         // optional [n_queries][n_points][n_members]: un-blended member outputs s_k (fitting)
+    float *acts_out;            // optional [n_members][tiles][kActFeat][128]: hidden activations h0|h1|h2|h3 (fitting backward)
     int n_members, n_symm;
     // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
     const float *anchors;       // [n_queries][n_members-1][3]
@@ -131,7 +133,8 @@ __device__ __forceinline__ void add_bias4(uint32_t (&r)[4], const float *bias)
     for (int e = 0; e < 4; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + b[e]);
 }
 
-template <bool PRUNE>
+// ACTS: also write the hidden activations for the fitting backward (separate instantiation: no cost on the query path)
+template <bool PRUNE, bool ACTS>
 __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -373,7 +376,16 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
 
             // first 96 layer-0 outputs (chunks part, part+4, part+8) -> spare TMEM columns.  Normally computed for the NEXT
             // member while the current member's layer-3 MMAs run; at the start of a tile it is computed in place.
-            auto layer0_a = [&](const float *r, float ccx, float ccy, float ccz) {
+            // hidden activations for the fitting backward (h = v / S), feature-major so that a warp store is one 128-byte line
+            auto save8 = [&](float *ab, int f0, int n_real, const float (&v)[8]) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < n_real) ab[(size_t)(f0 + e) * 128 + row] = v[e] * (1.0f / kS);
+            };
+            auto acts_of = [&](int member) -> float * {
+                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query + (tile % tiles_per_query)) * kActFeat * 128 : nullptr;
+            };
+            auto layer0_a = [&](const float *r, float ccx, float ccy, float ccz, float *ab) {
                 const float4 *l0a = reinterpret_cast<const float4 *>(r + kRecL0);
 #pragma unroll 1
                 for (int c = part; c < 12; c += kParts) {
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         const float t = fmaf(w.x, ccx, fmaf(w.y, ccy, fmaf(w.z, ccz, w.w)));
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
+                    if (ACTS) save8(ab, n0, 8, v);
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -427,8 +440,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                 };
 
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1
+                float *const ab = acts_of(m);
                 if (!a_done) {
-                    layer0_a(rec, cx, cy, cz);
+                    layer0_a(rec, cx, cy, cz, ab);
                     publish(&sm.a0a_ready);
                 }
 #pragma unroll 1
@@ -442,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
                     store_a8(tl + kColA0bHi + ((n0 - kNA) >> 1), tl + kColA0bLo + ((n0 - kNA) >> 1), v);
+                    if (ACTS) save8(ab, n0, 8, v);
                 }
                 {
                     const int n0 = 192 + 4 * part;               // rows >= 200 are zero: sp(0) meets zero weights
@@ -451,6 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         const float4 w = l0[n0 + e];
                         const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
+                    }
+                    if (ACTS && n0 < kH) {
+                        const float v8[8] = {v[0], v[1], v[2], v[3], 0.f, 0.f, 0.f, 0.f};
+                        save8(ab, n0, 4, v8);
                     }
                     store_a4(tl + kColA0bHi + ((n0 - kNA) >> 1), tl + kColA0bLo + ((n0 - kNA) >> 1), v);
                 }
@@ -471,6 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         add_bias4(r, rec + kRecB1 + n0);
                         if (part == 0) sp4(r, v);
                         else { v[0] = sp_t(__uint_as_float(r[0])); v[1] = cx; v[2] = cy; v[3] = cz; }
+                        if (ACTS) {
+                            const float v8[8] = {v[0], v[1], v[2], v[3], 0.f, 0.f, 0.f, 0.f};
+                            save8(ab, kH + n0, part == 0 ? 4 : 1, v8);          // h1 features 96..99 | 100
+                        }
                     }
                     store_a4(tl + kColA1Hi + (n0 >> 1), tl + kColA1Lo + (n0 >> 1), v);
                 }
@@ -484,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     float v[8];
                     sp8(r, v);
                     store_a8(tl + kColA1Hi + (n0 >> 1), tl + kColA1Lo + (n0 >> 1), v);
+                    if (ACTS) save8(ab, kH + n0, 8, v);
                     publish(&sm.a1_ready[grp]);
                 }
 
@@ -501,6 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     float v[8];
                     sp8(r, v);
                     store_a8(tl + kColA2Hi + (n0 >> 1), tl + kColA2Lo + (n0 >> 1), v);
+                    if (ACTS) save8(ab, kH + kN1 + n0, 8, v);
                 }
                 {
                     const int n0 = 192 + 4 * part;
@@ -511,6 +536,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     float v[4];
                     sp4(r, v);
                     store_a4(tl + kColA2Hi + (n0 >> 1), tl + kColA2Lo + (n0 >> 1), v);
+                    if (ACTS && n0 < kH) {
+                        const float v8[8] = {v[0], v[1], v[2], v[3], 0.f, 0.f, 0.f, 0.f};
+                        save8(ab, kH + kN1 + n0, 4, v8);
+                    }
                 }
                 publish(&sm.a2_ready);
 
@@ -525,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                         float nx, ny, nz;
                         member_coords(nrec, nx, ny, nz);
                         mbar_wait(&sm.a2_ready, m_ph);           // the A0a columns overlap D2: every warp must be done reading it
-                        layer0_a(nrec, nx, ny, nz);
+                        layer0_a(nrec, nx, ny, nz, acts_of(m + 1 + (__ffsll((long long)rest) - 1)));
                     }
                 }
 
@@ -546,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                     float v[8];
                     sp8(r, v);
+                    if (ACTS) save8(ab, 2 * kH + kN1 + n0, 8, v);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) acc = fmaf(v[e], w[e], acc);                  // w4 pad = 0
                 }
@@ -559,6 +589,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel(const Params p
                     const float w[4] = {w0.x, w0.y, w0.z, w0.w};
                     float v[4];
                     sp4(r, v);
+                    if (ACTS && n0 < kH) {
+                        const float v8[8] = {v[0], v[1], v[2], v[3], 0.f, 0.f, 0.f, 0.f};
+                        save8(ab, 2 * kH + kN1 + n0, 4, v8);
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc = fmaf(v[e], w[e], acc);
                 }
@@ -807,9 +841,10 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.weights = h->tc_weights.as<uint8_t>();
     p.recs = h->tc_consts.as<float>();
     p.xyz = q.xyz; p.axes = q.axes; p.res = q.res; p.first = q.first; p.total = q.total; p.n_points = q.n_points;
-    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out; p.members_out = q.members_out;
+    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out; p.members_out = q.members_out; p.acts_out = q.acts_out;
     p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
     const bool prune = h->tc_prune && !q.exact;
+    NPHM_REQUIRE(!q.acts_out || (q.n_queries == 1 && q.exact), "activation dump needs a single exact query");
     p.anchors = q.anchors; p.prune_tau = h->tc_prune_tau;
     p.blocked = 0; p.px0 = p.px1 = 0; p.by = p.bz = 1;
     long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;
@@ -825,7 +860,8 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.n_tiles = n_tiles;
     const int grid_x = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     const int smem = (int)sizeof(tc::Smem);
-    auto kern = prune ? tc::ensemble_tc_kernel<true> : tc::ensemble_tc_kernel<false>;
+    auto kern = q.acts_out ? tc::ensemble_tc_kernel<false, true>
+                           : (prune ? tc::ensemble_tc_kernel<true, false> : tc::ensemble_tc_kernel<false, false>);
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid_x, tc::kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
