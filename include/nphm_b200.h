@@ -191,6 +191,19 @@ int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev, long long 
                            float *loss_terms_dev, float *grad_out_dev,
                            void *workspace_dev, void *stream);
 
+/* Surface term of the joint fitter with gradients w.r.t. BOTH the identity code and the query points
+ * (reference src/NPHM/models/fitting.py:114-125: `sdf = decoder(xc, lat_rep_shape)`, `sdf[valid_ids]`, `l[l < clamp].mean()`):
+ *   loss = mean over { p : mask[p] != 0 and |sdf_p| < clamp } of |sdf_p|        (training-mode forward, no eval quirk)
+ * mask_dev (n_points bytes, may be NULL = all valid).  loss_terms_dev[0] = loss (NaN if nothing is kept, like torch),
+ * [5] = number of kept points, [1..4] = the latent regularisers (unweighted).  grad_latent_dev (lat_dim) and
+ * grad_points_dev (n_points*3, may be NULL) receive d loss / d latent (member inputs + anchors/mlp_pos + blend weights) and
+ * d loss / d point (local coordinates of every member + blend weights); both are zero when nothing is kept.
+ * The latent is not modified.  Same workspace as nphm_fit_identity_step.  Needs the tensor-core configuration when
+ * grad_points_dev is given. */
+int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, long long n_points, const float *latent_dev,
+                          const unsigned char *mask_dev, float clamp, float *loss_terms_dev,
+                          float *grad_latent_dev, float *grad_points_dev, void *workspace_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

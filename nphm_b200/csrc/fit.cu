@@ -50,6 +50,8 @@ struct Buffers {
     const float *anchors;           // n_loc x 3
     const float *cvec;              // [members][cvec_stride]
     float *member_s;                // n x members
+    const unsigned char *mask;      // optional n: 0 = the point is excluded from the loss (joint fitter: failed correspondences)
+    float *grad_points;             // optional n x 3: d loss / d point (accumulated over members with atomics)
     const float *acts;              // optional: hidden activations saved by the tensor-core forward, [member][tile128][feature][128]
     float *out, *S, *gsign;         // n each
     float *acc;                     // members x 2H   (sum delta0 | sum delta2)
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
 
     // ------------------------------------------------------------------ backward
     // upstream: g_s = g_out * w_k / (S + 1e-6),   g_out = lambda_surface * sign(sdf) * kept / n_kept
-    const float inv_count = 1.0f / b.stats[0];
+    const float inv_count = b.stats[0] > 0.f ? 1.0f / b.stats[0] : 0.f;      // nothing kept: zero gradient (torch: mean of empty)
     float gs[TM];
     float ba[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dim
     const bool has_anchor = m < d.n_loc;
     float ax = 0.f, ay = 0.f, az = 0.f;
     if (has_anchor) { ax = b.anchors[m * 3]; ay = b.anchors[m * 3 + 1]; az = b.anchors[m * 3 + 2]; }
-    // rows: h0 [0,H) | h1 [H, H+N1) | h2 | h3 | g_s (1 row)
+    // rows: h0 [0,H) | h1 [H, H+N1) | h2 | h3 | g_s (1 row) | d loss / d x (3 rows, only with grad_points)
     float *rh0 = sm, *rh1 = rh0 + (size_t)d.H * PP, *rh2 = rh1 + (size_t)d.N1 * PP, *rh3 = rh2 + (size_t)d.H * PP;
     float *rg = rh3 + (size_t)d.H * PP;
     {
@@ -329,12 +331,13 @@ __global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dim
     }
     // upstream gradient of this member's output per point, blend-path anchor gradient (same math as fit_member_kernel)
     if (warp == 0) {
-        const float inv_count = 1.0f / b.stats[0];
+        const float inv_count = b.stats[0] > 0.f ? 1.0f / b.stats[0] : 0.f;
         float ba[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const long long idx = p0 + lane * 2 + i;
             float gs = 0.f;
+            float gxb[3] = {0.f, 0.f, 0.f};
             if (idx < b.n) {
                 const float x = b.points[idx * 3], y = b.points[idx * 3 + 1], z = b.points[idx * 3 + 2];
                 const float g_out = lambda_surface * b.gsign[idx] * inv_count;
@@ -355,9 +358,14 @@ __global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dim
                     const float g_w = g_out * (s_k - b.out[idx]) / Sp;
                     const float coef = g_w * wk * (1.0f / 0.01f) * (-2.0f) * (r + 10e-6f) / r;
                     ba[0] += coef * dx; ba[1] += coef * dy; ba[2] += coef * dz;
+                    gxb[0] = -coef * dx; gxb[1] = -coef * dy; gxb[2] = -coef * dz;     // d w_k / d x = - d w_k / d a_k
                 }
             }
             rg[lane * 2 + i] = gs;
+            if (b.grad_points) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) rg[PP * (1 + a) + lane * 2 + i] = gxb[a];
+            }
         }
         if (has_anchor) {
 #pragma unroll
@@ -391,6 +399,33 @@ __global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dim
     __syncthreads();
     mma_layer_bwd(w.W[1] + (size_t)set * d.N1 * d.H, d.H, d.N1, d.H, 1.0f, rh1, rh0, warp, lane, nwarps);                   // delta0
     __syncthreads();
+    if (b.grad_points) {
+        // d loss / d x_p through this member's local coordinates: g_c(p) = W0x^T delta0(p) + W2x^T delta2(p) / sqrt2
+        // (x component negated for mirrored members), plus the blend-weight path stored above.  8 threads per point.
+        const int pt = threadIdx.x & 63, part = threadIdx.x >> 6;
+        const int in0 = 3 + d.C;
+        const float *W0 = w.W[0] + (size_t)set * d.H * in0;
+        const float *W2 = w.W[2] + (size_t)set * d.H * d.H + d.N1;
+        const int per = (d.H + 7) / 8;
+        float g[3] = {0.f, 0.f, 0.f};
+        for (int n = part * per; n < min(d.H, (part + 1) * per); ++n) {
+            const float d0 = rh0[(size_t)n * PP + pt], d2 = 0.70710678118654752f * rh2[(size_t)n * PP + pt];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                g[a] = fmaf(__ldg(W0 + (size_t)n * in0 + a), d0, fmaf(__ldg(W2 + (size_t)n * d.H + a), d2, g[a]));
+        }
+        const bool mirror = (m & 1) && m < 2 * d.n_symm;
+        if (mirror) g[0] = -g[0];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) atomicAdd(rg + PP * (1 + a) + pt, g[a]);
+        __syncthreads();
+        if (threadIdx.x < 3 * P) {
+            const int a = threadIdx.x / P, q = threadIdx.x % P;
+            const long long idx = p0 + q;
+            const float v = rg[PP * (1 + a) + q];
+            if (idx < b.n && v != 0.f) atomicAdd(b.grad_points + idx * 3 + a, v);
+        }
+    }
     float *acc = b.acc + (size_t)m * 2 * d.H;
     for (int n = warp; n < 2 * d.H; n += nwarps) {
         const float *row = (n < d.H ? rh0 + (size_t)n * PP : rh2 + (size_t)(n - d.H) * PP) + lane * 2;
@@ -425,7 +460,7 @@ __global__ void fit_blend_kernel(const Dims d, const Buffers b, float clamp)
         }
         const float out = __fdiv_rn(num, den + 1e-6f);
         const float l = fabsf(out);
-        const bool kept = l < clamp;
+        const bool kept = l < clamp && (!b.mask || b.mask[idx]);
         b.out[idx] = out; b.S[idx] = den;
         b.gsign[idx] = kept ? (out > 0.f ? 1.f : (out < 0.f ? -1.f : 0.f)) : 0.f;
         if (kept) { cnt = 1.f; sum = l; }
@@ -600,9 +635,10 @@ extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long 
     return floats * 4 + 1024;
 }
 
-extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
-                                      float *adam_m_dev, float *adam_v_dev, const nphm_fit_params *fp, int apply_update,
-                                      float *loss_terms_dev, float *grad_out_dev, void *workspace_dev, void *stream_)
+static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
+                         float *adam_m_dev, float *adam_v_dev, const nphm_fit_params *fp, int apply_update,
+                         float *loss_terms_dev, float *grad_out_dev, const unsigned char *mask_dev, float *grad_points_dev,
+                         void *workspace_dev, void *stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NPHM_REQUIRE(h && h->loaded, "nphm_fit_identity_step: weights not loaded");
@@ -654,6 +690,9 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
     p += (4 - ((p - ws) & 3)) & 3;                                  // 16-byte alignment of the activation block
     float *acts = p;
     b.acts = nullptr;
+    b.mask = mask_dev;
+    b.grad_points = grad_points_dev;
+    if (grad_points_dev) NPHM_CUDA_CHECK(cudaMemsetAsync(grad_points_dev, 0, (size_t)n_points * 3 * sizeof(float), stream));
 
     const int tiles = (int)ceil_div(n_points, fit::P);
     dim3 grid(tiles, h->n_members);
@@ -676,11 +715,15 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
     fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
     NPHM_CUDA_CHECK(cudaGetLastError());
     if (b.acts) {
-        const size_t bsm = (size_t)(3 * d.H + d.N1 + 1) * fit::PP * sizeof(float);
+        const size_t bsm = (size_t)(3 * d.H + d.N1 + 4) * fit::PP * sizeof(float);
         NPHM_REQUIRE(bsm <= 227 * 1024, "nphm_fit_identity_step: hidden width %d too large for the backward kernel", d.H);
         NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
         fit::fit_backward_mma_kernel<<<grid, fit::kThreads, bsm, stream>>>(d, w, b, fp->lambda_surface);
     } else {
+        if (grad_points_dev) {
+            set_error("gradient w.r.t. the points needs the tensor-core configuration (hidden 200, 4 layers, condition 96)");
+            return NPHM_ERR_UNSUPPORTED;
+        }
         fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
     }
     NPHM_CUDA_CHECK(cudaGetLastError());
@@ -701,4 +744,26 @@ extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev,
     fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
+}
+
+extern "C" int nphm_fit_identity_step(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
+                                      float *adam_m_dev, float *adam_v_dev, const nphm_fit_params *fp, int apply_update,
+                                      float *loss_terms_dev, float *grad_out_dev, void *workspace_dev, void *stream)
+{
+    return fit_step_impl(h, points_dev, n_points, latent_dev, adam_m_dev, adam_v_dev, fp, apply_update, loss_terms_dev,
+                         grad_out_dev, nullptr, nullptr, workspace_dev, stream);
+}
+
+extern "C" int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, long long n_points, const float *latent_dev,
+                                     const unsigned char *mask_dev, float clamp, float *loss_terms_dev,
+                                     float *grad_latent_dev, float *grad_points_dev, void *workspace_dev, void *stream)
+{
+    NPHM_REQUIRE(grad_latent_dev, "nphm_fit_surface_grad: grad_latent_dev is NULL");
+    nphm_fit_params fp{};
+    fp.lambda_surface = 1.0f;           // the regularisers of the latent code stay with the caller
+    fp.clamp = clamp;
+    fp.lr = 0.f;
+    fp.step = 1;
+    return fit_step_impl(h, points_dev, n_points, const_cast<float *>(latent_dev), nullptr, nullptr, &fp, 0, loss_terms_dev,
+                         grad_latent_dev, mask_dev, grad_points_dev, workspace_dev, stream);
 }

@@ -64,8 +64,12 @@ def _sample_observations(all_obs):
 
 
 def _fused_identity(decoder) -> bool:
+    """The fused step implements the training-mode forward, which is how the reference runs its fitters
+    (scripts/fitting/fitting_pointclouds.py:268 calls ``decoder_shape.train()`` first).  In eval mode the reference's
+    forward overwrites the last point of every row (EnsembledDeepSDF.py:257-259): that case takes the autograd path."""
     p = next(decoder.parameters())
-    return isinstance(decoder, FastEnsembleDeepSDFMirrored) and p.is_cuda and decoder.ensembled_deep_sdf.num_layers == 6
+    return (isinstance(decoder, FastEnsembleDeepSDFMirrored) and p.is_cuda and decoder.training
+            and decoder.ensembled_deep_sdf.num_layers == 6)
 
 
 class IdentityFitter:
@@ -95,6 +99,37 @@ class IdentityFitter:
                 self.v.data_ptr(), ctypes.byref(fp), int(apply_update), self.loss_terms.data_ptr(),
                 self.grad.data_ptr(), None, torch.cuda.current_stream(self.device).cuda_stream),
                 'nphm_fit_identity_step')
+
+
+class _FusedSurfaceLoss(torch.autograd.Function):
+    """``sdf = decoder(xc, z_id); sdf[valid].abs()[< clamp].mean()`` of the joint fitter (reference fitting.py:114-125) as
+    one native call (`nphm_fit_surface_grad`): tensor-core forward, analytic backward w.r.t. the identity code (member
+    inputs, anchors, blend weights) and w.r.t. the query points.  Autograd continues from the point gradient into the
+    implicit-differentiation correction and the deformation network."""
+
+    @staticmethod
+    def forward(ctx, xc, lat_rep_shape, valid, clamp, decoder):
+        dev = xc.device
+        pts = xc.detach().reshape(-1, 3).to(torch.float32).contiguous()
+        lat = lat_rep_shape.detach().reshape(-1).to(torch.float32).contiguous()
+        mask = valid.reshape(-1).to(torch.uint8).contiguous()
+        eng = decoder.engine()
+        terms = torch.empty(8, device=dev, dtype=torch.float32)
+        g_lat = torch.empty_like(lat)
+        g_pts = torch.empty_like(pts)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().nphm_fit_surface_grad(
+                eng.handle, pts.data_ptr(), pts.shape[0], lat.data_ptr(), mask.data_ptr(), float(clamp), terms.data_ptr(),
+                g_lat.data_ptr(), g_pts.data_ptr(), None, torch.cuda.current_stream(dev).cuda_stream),
+                'nphm_fit_surface_grad')
+        ctx.save_for_backward(g_lat, g_pts)
+        ctx.shapes = (xc.shape, lat_rep_shape.shape)
+        return terms[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g_lat, g_pts = ctx.saved_tensors
+        return grad_out * g_pts.reshape(ctx.shapes[0]), grad_out * g_lat.reshape(ctx.shapes[1]), None, None, None
 
 
 def inference_identity_space(decoder,
@@ -183,8 +218,9 @@ def inference_iterative_root_finding_joint(decoder,
                                            lr_scale=1):
     """Joint identity + expression fitting with Broyden correspondences (reference :14-177).
 
-    Autograd implementation on top of the drop-in modules: the no-grad network evaluations inside the Broyden
-    search run on the fused kernels, the loss/backward part uses the composite path.  Returns
+    The correspondence search runs on the device (`nphm_mlp_broyden_search`), the surface term and its gradients w.r.t. the
+    identity code and the canonical points come from one native call (`nphm_fit_surface_grad`); the deformation network's
+    part of the chain (implicit differentiation of the root, Jacobians) stays on autograd.  Returns
     ``(lat_rep (n_obs,1,E), lat_rep_shape (1,1,D), anchors)``."""
     device = all_obs[0].device
     num_observations = len(all_obs)
@@ -222,14 +258,19 @@ def inference_iterative_root_finding_joint(decoder,
         correction = preds_posed - preds_posed.detach()
         correction = torch.einsum('bnij,bnj->bni', -grad_inv.detach(), correction)
         xc = p_corresp + correction
-        if has_local:
-            sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, 1, 1), None)
+        if has_local and _fused_identity(decoder) and xc.is_cuda:
+            surface = _FusedSurfaceLoss.apply(xc, lat_rep_shape, search_result['valid_ids'],
+                                              _clamp_for_iteration(j, step_scale), decoder)
         else:
-            sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, n_point, 1), None)
-        sdf = sdf[search_result['valid_ids'], :]
-        l = sdf.abs()
-        l = l[l < _clamp_for_iteration(j, step_scale)]
-        loss_dict = {'surface': l.mean(),
+            if has_local:
+                sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, 1, 1), None)
+            else:
+                sdf, _ = decoder(xc, lat_rep_shape.repeat(nb, n_point, 1), None)
+            sdf = sdf[search_result['valid_ids'], :]
+            l = sdf.abs()
+            l = l[l < _clamp_for_iteration(j, step_scale)]
+            surface = l.mean()
+        loss_dict = {'surface': surface,
                      'reg_expr': (torch.norm(lat_rep[obs_idx, :, :], dim=-1) ** 2).mean()}
         loss_dict.update(_latent_regularisers(decoder, lat_rep_shape))
         loss = 0

@@ -152,3 +152,39 @@ def test_device_broyden_search_edge_cases(cuda_device):
     assert torch.allclose(diff, torch.full_like(diff, 0.05 * 3 ** 0.5), atol=1e-5)
     x, diff, valid, steps = eng.broyden_search(obs[:, :0], cond, x0[:, :0], eye[:, :0])
     assert x.shape == (1, 0, 3) and valid.numel() == 0
+
+
+def test_surface_loss_gradients_wrt_latent_and_points(cuda_device):
+    """nphm_fit_surface_grad against autograd through the (reference-pinned) composite module: loss value, kept count,
+    d loss / d z_id and d loss / d points, with a validity mask and a clamp that both drop points."""
+    from conftest import sample_latent
+    from nphm_b200.models.fitting import _FusedSurfaceLoss
+    dec = make_ensemble(0, device=cuda_device).train()
+    torch.manual_seed(5)
+    xc = (torch.randn(2, 700, 3, device=cuda_device) * 0.15 + torch.tensor([0.0, 0.05, -0.1], device=cuda_device))
+    valid = torch.rand(2, 700, device=cuda_device) > 0.2
+    z0 = sample_latent(3).to(cuda_device).reshape(1, 1, -1)
+    for clamp in (0.1, 0.02):
+        xa = xc.clone().requires_grad_(True); za = z0.clone().requires_grad_(True)
+        sdf, _ = dec(xa, za.repeat(2, 1, 1), None)                       # autograd composite (requires_grad inputs)
+        l = sdf[valid, :].abs()
+        keep = l < clamp
+        ref = l[keep].mean()
+        ref.backward()
+        xb = xc.clone().requires_grad_(True); zb = z0.clone().requires_grad_(True)
+        out = _FusedSurfaceLoss.apply(xb, zb, valid, clamp, dec)
+        (3.0 * out).backward()
+        assert int(keep.sum()) > 50
+        assert abs(out.item() - ref.item()) < 1e-6
+        gz_ref, gx_ref = za.grad.reshape(-1).cpu().numpy(), xa.grad.cpu().numpy()
+        gz, gx = zb.grad.reshape(-1).cpu().numpy() / 3.0, xb.grad.cpu().numpy() / 3.0
+        assert _rel(gz, gz_ref) < 2e-4, _rel(gz, gz_ref)
+        assert _rel(gx, gx_ref) < 2e-4, _rel(gx, gx_ref)
+        # points outside the mask / clamp receive exactly zero gradient
+        dropped = ~(valid & (sdf.detach()[..., 0].abs() < clamp))
+        assert np.abs(gx[dropped.cpu().numpy()]).max() == 0.0
+    # nothing kept: NaN loss like torch's mean of an empty tensor, zero gradients
+    xb = xc.clone().requires_grad_(True); zb = z0.clone().requires_grad_(True)
+    out = _FusedSurfaceLoss.apply(xb, zb, torch.zeros_like(valid), 0.1, dec)
+    out.backward()
+    assert torch.isnan(out) and float(xb.grad.abs().max()) == 0.0 and float(zb.grad.abs().max()) == 0.0

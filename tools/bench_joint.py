@@ -21,7 +21,7 @@ def main():
     from conftest import make_ensemble, make_deformation
     from nphm_b200.models.fitting import inference_iterative_root_finding_joint
     dev = torch.device('cuda', 0)
-    dec = make_ensemble(0, device=dev).eval()
+    dec = make_ensemble(0, device=dev).train()               # fitting_pointclouds.py:268
     dfn = make_deformation(device=dev)
     with torch.no_grad():                                   # small deformations, like a trained field near the neutral pose
         dfn.defDeepSDF.lin6.weight.mul_(0.05); dfn.defDeepSDF.lin6.bias.mul_(0.05)
