@@ -113,6 +113,36 @@ class DeepSDF(nn.Module):
         return h
 
 
+def _input_jacobian(backbone: DeepSDF, xyz, cond):
+    """Forward-mode derivative of the backbone output w.r.t. ``xyz`` (the condition does not depend on the point):
+    returns ``(out  ... x out_dim,  J  ... x out_dim x 3)``.  Same function as three reverse-mode passes through
+    :meth:`DeepSDF._forward_composite` (what the reference's ``jac`` does, diff_operators.py:26-54) at a third of the
+    launches: the three tangents ride through the layers as one batched matmul,
+    ``T_{l+1} = sigmoid(beta z_l) * (T_l W_l^T)``."""
+    if cond.shape[-2] == 1 and xyz.shape[-2] != 1:
+        cond = cond.expand(*xyz.shape[:-1], cond.shape[-1])
+    inp = torch.cat([xyz, cond], dim=-1)
+    h, T = inp, None
+    last = backbone.num_layers - 2
+    for layer in range(last + 1):
+        lin = getattr(backbone, 'lin' + str(layer))
+        W = lin.weight
+        if layer in backbone.skip_in:
+            wh = h.shape[-1]
+            h = torch.cat([h, inp], dim=-1) / _SQRT2
+            dz = (torch.matmul(T, W[:, :wh].t()) + W[:, wh:wh + 3].t()) / _SQRT2
+        elif T is None:
+            dz = W[:, :3].t().expand(*xyz.shape[:-1], 3, W.shape[0])
+        else:
+            dz = torch.matmul(T, W.t())
+        z = lin(h)
+        if layer < last:
+            h = backbone.activation(z)
+            T = torch.sigmoid(backbone.beta * z).unsqueeze(-2) * dz
+        else:
+            return z, dz.transpose(-1, -2)
+
+
 class DeformationNetwork(nn.Module):
     """Forward deformation field F_ex(x; z_ex, z_id): canonical point -> offset.
 
@@ -212,6 +242,17 @@ class DeformationNetwork(nn.Module):
             return torch.cat([combined.unsqueeze(1).expand(B, N, combined.shape[-1]),
                               lat_rep[..., -E:].expand(B, N, E)], dim=-1)
         raise ValueError('Unknown mode')
+
+    def offset_jacobian(self, xyz, lat_rep, anchors):
+        """``d offsets / d xyz`` (B x N x 3 x 3) by forward-mode differentiation, or ``None`` when the fast path does not
+        apply (condition depends on the point, positional encoding, ReLU backbone, training-mode noise)."""
+        backbone = self.defDeepSDF
+        if (self.training or self.mode not in ('compress', 'expr_only', 'glob_only') or backbone.num_freq_bands is not None
+                or backbone.beta <= 0 or 0 in backbone.skip_in or xyz.dim() != 3):
+            return None
+        cond = self._condition(xyz, lat_rep, anchors, per_point=lat_rep.shape[1] != 1)
+        _, J = _input_jacobian(backbone, xyz, cond)
+        return J[..., :3, :]
 
     def forward(self,
                 xyz: torch.Tensor,

@@ -3,7 +3,9 @@
   * ``jac``       src/NPHM/models/diff_operators.py:26-54  - 3x3 Jacobian of x + F_ex(x) w.r.t. x
   * ``gradient``  src/NPHM/models/diff_operators.py:69-79  - spatial gradient of a scalar field (keeps the graph)
 
-Like the reference, both set ``requires_grad_(True)`` on their input as a side effect.
+Like the reference, both set ``requires_grad_(True)`` on their input as a side effect.  For the drop-in
+``DeformationNetwork`` ``jac`` evaluates the same Jacobian by forward-mode differentiation (no graph is returned; the
+reference's callers - ``search`` and the joint fitter - detach it anyway).
 """
 import torch
 
@@ -11,6 +13,13 @@ import torch
 def jac(decoder_expr, xc, cond, anchors):
     """Returns d(xc + F_ex(xc)) / d xc as ``B x N x 3 x 3`` (row i = gradient of output i)."""
     xc.requires_grad_(True)
+    fast = getattr(decoder_expr, 'offset_jacobian', None)
+    if fast is not None:
+        # forward-mode fast path of the drop-in DeformationNetwork (its callers only use the value of the Jacobian)
+        with torch.no_grad():
+            J = fast(xc.detach(), cond.detach(), anchors.detach() if anchors is not None else None)
+        if J is not None:
+            return J + torch.eye(3, device=J.device, dtype=J.dtype)
     xd, _ = decoder_expr(xc, cond, anchors)
     xd = xc + xd
     rows = []

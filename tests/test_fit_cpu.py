@@ -84,3 +84,29 @@ def test_joint_fitter_mirror_follows_reference():
     close_id = np.abs(z_id.detach().numpy().reshape(-1) - g['z_id_before'][2]) < 2e-4
     close_ex = np.abs(z_ex.detach().numpy().reshape(3, 200) - g['z_ex_before'][2]) < 2e-4
     assert close_id.mean() > 0.97 and close_ex.mean() > 0.97, (close_id.mean(), close_ex.mean())
+
+
+def test_forward_mode_jacobian_equals_reverse_mode():
+    """`jac` fast path (forward-mode through the DeformationNetwork) vs three reverse-mode passes (the reference's way)."""
+    import torch
+    from conftest import make_deformation
+    from nphm_b200.models import diff_operators as D
+    dfn = make_deformation()
+    torch.manual_seed(1)
+    xc = torch.randn(2, 40, 3) * 0.2
+    cond = torch.randn(2, 1, 1344 + 200).repeat(1, 40, 1) * 0.1
+    anchors = torch.randn(2, 40, 39, 3) * 0.1
+    J_fast = D.jac(dfn, xc.clone(), cond, anchors)
+    saved = dfn.offset_jacobian
+    dfn.offset_jacobian = lambda *a, **k: None            # force the reverse-mode path
+    try:
+        J_ref = D.jac(dfn, xc.clone(), cond, anchors)
+    finally:
+        dfn.offset_jacobian = saved
+    assert J_fast.shape == J_ref.shape == (2, 40, 3, 3)
+    assert float((J_fast - J_ref).abs().max()) < 2e-6
+    dfn.train()
+    try:
+        assert dfn.offset_jacobian(xc, cond, anchors) is None     # training-mode noise: reverse mode only
+    finally:
+        dfn.eval()
