@@ -127,7 +127,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', os.environ.get('NPHM_BENCH_SAMPLE_MS', '100')],
+                                          '--format=csv,noheader,nounits', '-lms', os.environ.get('NPHM_BENCH_SAMPLE_MS', '200')],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -238,6 +238,8 @@ def main():
         kev[i][2].record()
         launches['n'] += 8
         n_tris = t.shape[0]
+        del v, t                        # like the warm-up: the mesh buffers go back to torch's caching allocator (no cudaMalloc
+                                        # for a second generation of buffers inside the timed region)
         flush.zero_()                   # L2 flush between timed iterations (inside the timed region)
         kev[i][3].record()
     ev[1].record()
