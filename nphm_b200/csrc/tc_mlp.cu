@@ -17,7 +17,9 @@
 // D_a = TMEM[0,256) and D_b = TMEM[256,512), each filled by one long run of SS-form MMAs (an accumulator switch
 // costs ~200 cycles, an M = 64 MMA costs max(70, N/2) cycles: profiles/r01_mma_microbench.txt).  Weights stream
 // through a 5-slot ring of (N_half x 16) fp16 hi|lo slabs.  Same 3-pass fp16 split and log2-unit softplus as the
-// ensemble kernel.  M = 64 uses TMEM lanes (r % 16) + 32 * (r / 16): lanes 16-31 of every warp idle in the epilogue.
+// ensemble kernel.  M = 64 uses TMEM lanes (r % 16) + 32 * (r / 16): the epilogue therefore reads the accumulator with the
+// 16-lane shape tcgen05.ld.16x256b (thread = rows l/4 and l/4+8, column pairs 2*(l%4)), which keeps all 32 lanes of a warp
+// busy and makes the fp16-pair stores of a warp one contiguous 128-byte line of the chunk-major A operand.
 #include "engine.cuh"
 #include "tc_common.cuh"
 
@@ -68,23 +70,20 @@ __device__ __forceinline__ int d_col(int t, int n)
     const int nh = layer_nh(t);
     return n < nh ? n : 256 + (n - nh);
 }
-__device__ __forceinline__ void store_a_chunk(Smem &sm, int chunk, int row, bool active, const float (&v)[8])
+// 16 lanes x 16 accumulator columns: r[4g + 0/1] = (row l/4, cols 8g + 2(l%4) + 0/1), r[4g + 2/3] = same columns, row l/4 + 8
+__device__ __forceinline__ void tc_ld16x16(uint32_t taddr, uint32_t (&r)[8])
 {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    if (active) {
-        *reinterpret_cast<uint4 *>(sm.a_hi + (size_t)chunk * 1024 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(sm.a_lo + (size_t)chunk * 1024 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void init_d_chunk(uint32_t tl, int t, int chunk, const float *__restrict__ bias)
+// one fp16 pair (hi and lo planes) of row `row`, K chunk `chunk`, pair index j (K columns 8*chunk + 2j, +1)
+__device__ __forceinline__ void store_a_pair(Smem &sm, int chunk, int row, int j, float v0, float v1)
 {
-    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + chunk * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + chunk * 8 + 4));
-    const uint32_t r[8] = {__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w),
-                           __float_as_uint(b1.x), __float_as_uint(b1.y), __float_as_uint(b1.z), __float_as_uint(b1.w)};
-    tc_st8(tl + d_col(t, chunk * 8), r);
+    uint32_t hi, lo;
+    split2(v0, v1, hi, lo);
+    *reinterpret_cast<uint32_t *>(sm.a_hi + (size_t)chunk * 1024 + row * 16 + j * 4) = hi;
+    *reinterpret_cast<uint32_t *>(sm.a_lo + (size_t)chunk * 1024 + row * 16 + j * 4) = lo;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const Params p)
@@ -156,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const Params p)
                             const uint32_t b = smem_u32(sm.slabs[slot]);
                             const uint64_t b_hi = make_desc(b, 128, 256), b_lo = make_desc(b + nh * 32, 128, 256);
                             const uint64_t ah = make_desc(a_hi + j * 2048, 1024, 128), al = make_desc(a_lo + j * 2048, 1024, 128);
-                            tc_mma_ss(d, ah, b_hi, idesc, 1);
+                            tc_mma_ss(d, ah, b_hi, idesc, j == 0 ? 0 : 1);      // first k-step overwrites: the bias is added in the epilogue
                             tc_mma_ss(d, ah, b_lo, idesc, 1);
                             tc_mma_ss(d, al, b_hi, idesc, 1);
                             tc_commit(&sm.slab_empty[slot]);
@@ -169,111 +168,131 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const Params p)
         }
     } else {
         // =========================================================================== compute / epilogue warps
-        // warp = (TMEM lane quarter q, column group part); lanes 0-15 hold rows 16q..16q+15 of the tile, lanes 16-31 idle.
-        // 8-column chunk c of every layer belongs to part c & 3.
+        // warp = (TMEM lane quarter q, column group part).  Rows 16q..16q+15 of the tile sit in lanes 0-15 of the quarter; a
+        // thread owns rows rA = 16q + l/4 and rB = rA + 8 and the column pairs 2*(l%4) of every 8-column group it loads.
+        // 16-column block b of a layer belongs to part b & 3.
         const int q = warp & 3, part = warp >> 2;
-        const bool active = lane < 16;
-        const int row = q * 16 + (lane & 15);
+        const int j = lane & 3;
+        const int rowA = q * 16 + (lane >> 2), rowB = rowA + 8;
+        const int row0 = q * 16 + (lane & 15), half0 = lane >> 4;      // layer 0: (row, 4-element half of a chunk)
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t d_ph = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int qi = (int)(tile / tiles_per_query);
-            const long long idx = (tile - (long long)qi * tiles_per_query) * 64 + row;
-            const bool valid = active && idx < p.n_points;
-            const float *pp = p.xyz + ((size_t)qi * p.n_points + (idx < p.n_points ? idx : 0)) * 3;
-            const float cx = kS * pp[0], cy = kS * pp[1], cz = kS * pp[2];      // coordinates in log2 units
+            const long long base = (tile - (long long)qi * tiles_per_query) * 64;
+            auto coords = [&](int row, float &x, float &y, float &z) {
+                const long long idx = base + row;
+                const float *pp = p.xyz + ((size_t)qi * p.n_points + (idx < p.n_points ? idx : 0)) * 3;
+                x = kS * pp[0]; y = kS * pp[1]; z = kS * pp[2];         // coordinates in log2 units
+            };
             const float *rec = p.recs + (size_t)qi * kRecFloats;
 
-            // ---------------- layer 0 on CUDA cores -> A of tensor layer 0
+            // ---------------- layer 0 on CUDA cores -> A of tensor layer 0 (all 32 lanes: 16 rows x 2 chunk halves)
             {
+                float cx, cy, cz;
+                coords(row0, cx, cy, cz);
                 const float4 *l0 = reinterpret_cast<const float4 *>(rec + kRecL0);
 #pragma unroll 1
                 for (int c = part; c < 64; c += kParts) {
-                    float v[8];
+                    float v[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 w = __ldg(l0 + c * 8 + e);
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 w = __ldg(l0 + c * 8 + half0 * 4 + e);
                         const float t = fmaf(w.x, cx, fmaf(w.y, cy, fmaf(w.z, cz, w.w)));
                         v[e] = (e & 1) ? sp_t_poly(t) : sp_t(t);
                     }
-                    store_a_chunk(sm, c, row, active, v);
-                    init_d_chunk(tl, 0, c, rec + rec_bias_off(0));
+                    store_a_pair(sm, c, row0, half0 * 2, v[0], v[1]);
+                    store_a_pair(sm, c, row0, half0 * 2 + 1, v[2], v[3]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a_ready);
 
-            float acc[3] = {0.f, 0.f, 0.f};
+            float axA, ayA, azA, axB, ayB, azB;
+            coords(rowA, axA, ayA, azA);
+            coords(rowB, axB, ayB, azB);
+            float accA[3] = {0.f, 0.f, 0.f}, accB[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int t = 0; t < kTL; ++t) {
-                const int n_chunks = layer_np(t) / 8;
+                const int n_blocks = layer_np(t) / 16;
+                const float *bias = rec + rec_bias_off(t);
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = part; c < n_chunks; c += kParts) {
+                for (int b = part; b < n_blocks; b += kParts) {
+                    const int n0 = b * 16;
                     uint32_t r[8];
-                    tc_ld8(tl + d_col(t, c * 8), r);
+                    tc_ld16x16(tl + d_col(t, n0), r);
                     tc_wait_ld();
-                    float v[8];
-                    sp8(r, v);
-                    if (t == 1) {
-                        // 277 outputs; K of the skip layer = [h2 (277), x (3), zero padding]
-                        if (c == 34) { v[5] = cx; v[6] = cy; v[7] = cz; }
-                        if (c == 35) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    for (int g = 0; g < 2; ++g) {
+                        const int n = n0 + 8 * g + 2 * j;                         // this thread's column pair of group g
+                        const float2 bb = __ldg(reinterpret_cast<const float2 *>(bias + n));
+                        float vA0 = sp_t(__uint_as_float(r[4 * g + 0]) + bb.x), vA1 = sp_t_poly(__uint_as_float(r[4 * g + 1]) + bb.y);
+                        float vB0 = sp_t(__uint_as_float(r[4 * g + 2]) + bb.x), vB1 = sp_t(__uint_as_float(r[4 * g + 3]) + bb.y);
+                        if (t == 1) {
+                            // 277 outputs; K of the skip layer = [h2 (277), x (3), zero padding to 288]
+                            if (n == 276) { vA1 = axA; vB1 = axB; }
+                            else if (n == 278) { vA0 = ayA; vA1 = azA; vB0 = ayB; vB1 = azB; }
+                            else if (n >= 280) { vA0 = vA1 = vB0 = vB1 = 0.f; }
                         }
-                    }
-                    if (t < kTL - 1) {
-                        store_a_chunk(sm, c, row, active, v);
-                    } else {
-                        const float *w6 = rec + kRecW6 + c * 8;
+                        if (t < kTL - 1) {
+                            store_a_pair(sm, n >> 3, rowA, j, vA0, vA1);
+                            store_a_pair(sm, n >> 3, rowB, j, vB0, vB1);
+                        } else {
+                            const float *w6 = rec + kRecW6 + n;
 #pragma unroll
-                        for (int o = 0; o < 3; ++o) {
-                            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w6 + o * kH));
-                            const float4 w1 = __ldg(reinterpret_cast<const float4 *>(w6 + o * kH + 4));
-                            acc[o] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, acc[o]))));
-                            acc[o] = fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, acc[o]))));
+                            for (int o = 0; o < 3; ++o) {
+                                const float2 w = __ldg(reinterpret_cast<const float2 *>(w6 + o * kH));
+                                accA[o] = fmaf(vA0, w.x, fmaf(vA1, w.y, accA[o]));
+                                accB[o] = fmaf(vB0, w.x, fmaf(vB1, w.y, accB[o]));
+                            }
                         }
                     }
                 }
                 if (t < kTL - 1) {
-                    // the next layer's D columns map differently: all reads of this layer first (4 warps of the quarter)
-                    tc_fence_before();
-                    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");
-                    tc_fence_after();
-                    const int next_chunks = layer_np(t + 1) / 8;
-#pragma unroll 1
-                    for (int c = part; c < next_chunks; c += kParts) init_d_chunk(tl, t + 1, c, rec + rec_bias_off(t + 1));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.a_ready);
                 }
             }
-            // ---------------- output layer: reduce the 3 partial dot products over the column groups
-            if (part != 0 && active) {
-                sm.partial[part - 1][row][0] = acc[0]; sm.partial[part - 1][row][1] = acc[1]; sm.partial[part - 1][row][2] = acc[2];
+            // ---------------- output layer: reduce the partial dot products over the column pairs of a row (4 lanes) and
+            // over the column groups (4 warps of the quarter)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                accA[o] += __shfl_xor_sync(0xffffffffu, accA[o], 1); accA[o] += __shfl_xor_sync(0xffffffffu, accA[o], 2);
+                accB[o] += __shfl_xor_sync(0xffffffffu, accB[o], 1); accB[o] += __shfl_xor_sync(0xffffffffu, accB[o], 2);
+            }
+            if (part != 0 && j == 0) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o) { sm.partial[part - 1][rowA][o] = accA[o]; sm.partial[part - 1][rowB][o] = accB[o]; }
             }
             tc_fence_before();
             asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");
             tc_fence_after();
-            if (part == 0 && valid) {
-                float *o = p.out + ((size_t)qi * p.n_points + idx) * 3;
+            if (part == 0 && j == 0) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    float s = acc[j] + __ldg(rec + kRecB6 + j);
+                for (int h = 0; h < 2; ++h) {
+                    const int row = h ? rowB : rowA;
+                    const long long idx = base + row;
+                    if (idx < p.n_points) {
+                        float *o = p.out + ((size_t)qi * p.n_points + idx) * 3;
 #pragma unroll
-                    for (int i = 0; i < kParts - 1; ++i) s += sm.partial[i][row][j];
-                    o[j] = s;
+                        for (int c = 0; c < 3; ++c) {
+                            float sum = (h ? accB[c] : accA[c]) + __ldg(rec + kRecB6 + c);
+#pragma unroll
+                            for (int i = 0; i < kParts - 1; ++i) sum += sm.partial[i][row][c];
+                            o[c] = sum;
+                        }
+                    }
                 }
             }
-            // the partial buffer is reused by the next tile: its writers pass 5 layer barriers first
+            // the partial buffer is reused by the next tile: a second bar.sync keeps its readers ahead of the next writers
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");
         }
     }
 
