@@ -78,6 +78,12 @@ def cpu_reference_sample(res, n_chunks, with_mc=True):
     return total / est_step, detail
 
 
+def workload_name(res):
+    """One name for both arms of the benchmark (BASELINE.json configs[1] at res = 256)."""
+    return ('single-head %d^3 grid SDF (40-member ensemble, seeded random weights) + marching cubes, random latent; '
+            'one head per GPU' % res)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -101,8 +107,7 @@ def run_reference_arm(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * args.res ** 3 / value, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'single-head %d^3 grid SDF (40-member ensemble) + marching cubes, random latent' % args.res,
-                   'res': args.res, 'nbatch_points': CHUNK},
+        'config': {'workload': workload_name(args.res), 'res': args.res, 'nbatch_points': CHUNK},
         'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample,
                          'detail': detail},
         'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -333,8 +338,7 @@ def main():
             'metric': 'sdf_query_points_per_s', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'single-head %d^3 grid SDF (40-member ensemble, seeded random weights) + marching '
-                                   'cubes, random latent; one head per GPU' % res,
+            'config': {'workload': workload_name(res),
                        'res': res, 'nbatch_points': CHUNK, 'impl': args.impl, 'l2': 'flushed between iterations (256 MB write)',
                        'triangles': int(n_tris)},
             'meshes_per_s': world / (ms_per_step * 1e-3),
