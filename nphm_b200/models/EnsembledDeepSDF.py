@@ -25,8 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native
-
-_SQRT2 = math.sqrt(2.0)
+from . import _composite
 
 
 def _member_to_set(ensemble_size: int, n_symm: int) -> torch.Tensor:
@@ -66,12 +65,8 @@ class EnsembledLinear(nn.Module):
                     nn.init.uniform_(self.bias[s], -bound, bound)
 
     def forward(self, input):
-        # input: A x M x D_in  ->  A x M x D_out
-        w = self.weight.index_select(0, self._set_of_member)            # A x D_out x D_in
-        out = torch.matmul(input, w.transpose(1, 2))
-        if self.bias is not None:
-            out = out + self.bias.index_select(0, self._set_of_member).unsqueeze(1)
-        return out
+        """A x M x D_in -> A x M x D_out."""
+        return _composite.ensembled_affine(input, self.weight, self.bias, self._set_of_member)
 
 
 class EnsembledDeepSDF(nn.Module):
@@ -97,18 +92,11 @@ class EnsembledDeepSDF(nn.Module):
         self.activation = nn.Softplus(beta=100)
 
     def forward(self, xyz, lat_rep):
-        # xyz: A x B x nP x 3 ; lat_rep: A x B x nP x F  ->  A x B x nP x out_dim
+        """xyz: A x B x nP x 3, lat_rep: A x B x nP x F  ->  A x B x nP x out_dim (A = ensemble members)."""
         A, B, nP, _ = xyz.shape
+        layers = [getattr(self, 'lin%d' % i) for i in range(self.num_layers - 1)]
         inp = torch.cat([xyz, lat_rep], dim=-1).reshape(A, B * nP, -1)
-        h = inp
-        last = self.num_layers - 2
-        for layer in range(last + 1):
-            if layer in self.skip_in:
-                h = torch.cat([h, inp], dim=-1) / _SQRT2
-            h = getattr(self, 'lin' + str(layer))(h)
-            if layer < last:
-                h = self.activation(h)
-        return h.reshape(A, B, nP, -1)
+        return _composite.skip_mlp(inp, layers, self.skip_in, self.activation).reshape(A, B, nP, -1)
 
 
 def sample_point_feature(q, p, fea, var=0.1 ** 2, background=False):
@@ -117,12 +105,7 @@ def sample_point_feature(q, p, fea, var=0.1 ** 2, background=False):
     q: B x N x 3, p: B x K x 3, fea: B x N x K(+1) x C  ->  B x N x C.
     ``-(|p-q| + 1e-5)^2 / var`` logits, optional constant background logit ``-0.2/var``,
     normalised by ``sum + 1e-6``."""
-    dist = -((p.unsqueeze(1) - q.unsqueeze(2)).norm(dim=3) + 10e-6) ** 2
-    if background:
-        dist = torch.cat([dist, torch.full_like(dist[:, :, :1], -0.2)], dim=-1)
-    weight = (dist / var).exp()
-    weight = weight / (weight.sum(dim=2, keepdim=True) + 1e-6)
-    return (weight.unsqueeze(-1) * fea).sum(dim=2)
+    return _composite.gaussian_blend(q, p, fea, var, background)
 
 
 class FastEnsembleDeepSDFMirrored(nn.Module):
@@ -213,30 +196,4 @@ class FastEnsembleDeepSDFMirrored(nn.Module):
         return self._forward_composite(xyz, lat_rep)
 
     def _forward_composite(self, xyz, lat_rep):
-        B, N, _ = xyz.shape
-        K, G, L = self.num_kps, self.lat_dim_glob, self.lat_dim_loc
-        if lat_rep.shape[1] == 1:
-            lat_rep = lat_rep.expand(B, N, self.lat_dim)
-
-        anchors = self.mlp_pos(lat_rep[:, 0, :G]).view(B, K, 3)
-        anchors = anchors + self.mean_anchors(xyz.device, anchors.dtype).unsqueeze(0)
-
-        # local coordinates; the last member works in global coordinates
-        origin = torch.cat([anchors, torch.zeros_like(anchors[:, :1])], dim=1)       # B x (K+1) x 3
-        coords = xyz.unsqueeze(2) - origin.unsqueeze(1)                               # B x N x (K+1) x 3
-        flip = torch.ones(K + 1, 3, device=xyz.device, dtype=xyz.dtype)
-        flip[1:2 * self.num_symm_pairs:2, 0] = -1.0                                   # mirror odd symmetric members
-        coords = coords * flip
-
-        z_glob = lat_rep[:, :, :G].unsqueeze(2).expand(B, N, K + 1, G)
-        z_loc = lat_rep[:, :, G:].reshape(B, N, K + 1, L)
-        cond = torch.cat([z_glob, z_loc], dim=-1)
-
-        sdf = self.ensembled_deep_sdf(coords.permute(2, 0, 1, 3), cond.permute(2, 0, 1, 3))
-        if not self.training:
-            # reference :260-261 indexes the POINT axis: the last point of the call gets s_k = 1
-            sdf = sdf.clone()
-            sdf[:, :, -1, 0] = 1
-        sdf = sdf.permute(1, 2, 0, 3)
-        pred = sample_point_feature(xyz[..., :3], anchors, sdf, background=True, var=0.1 ** 2)
-        return pred, anchors
+        return _composite.ensemble_sdf(self, xyz, lat_rep)

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native
+from . import _composite
 from .EnsembledDeepSDF import sample_point_feature  # same function in the reference (:92-115)
 
 _SQRT2 = math.sqrt(2.0)
@@ -101,16 +102,8 @@ class DeepSDF(nn.Module):
             xyz = torch.cat(feats, dim=-1)
         if lat_rep.shape[-2] == 1 and xyz.shape[-2] != 1:
             lat_rep = lat_rep.expand(*xyz.shape[:-1], lat_rep.shape[-1])
-        inp = torch.cat([xyz, lat_rep], dim=-1)
-        h = inp
-        last = self.num_layers - 2
-        for layer in range(last + 1):
-            if layer in self.skip_in:
-                h = torch.cat([h, inp], dim=-1) / _SQRT2
-            h = getattr(self, 'lin' + str(layer))(h)
-            if layer < last:
-                h = self.activation(h)
-        return h
+        layers = [getattr(self, 'lin%d' % i) for i in range(self.num_layers - 1)]
+        return _composite.skip_mlp(torch.cat([xyz, lat_rep], dim=-1), layers, self.skip_in, self.activation)
 
 
 def _input_jacobian(backbone: DeepSDF, xyz, cond):

@@ -13,38 +13,39 @@ from .diff_operators import gradient, jac
 
 
 def broyden(g, x_init, J_inv_init, max_steps=50, cvg_thresh=1e-5, dvg_thresh=1, eps=1e-6):
-    """Batched Broyden root finder for g(x) = 0.  x: N x D x 1, J_inv: N x D x D.
-    Returns {'result': best x, 'diff': |g| at the best x, 'valid_ids': converged mask}."""
-    x = x_init.clone().detach()
-    J_inv = J_inv_init.clone().detach()
-    active = torch.ones(x.shape[0], dtype=torch.bool, device=x.device)
-    gx = g(x, mask=active)
-    update = -J_inv.bmm(gx)
-    x_opt = x
-    best = torch.linalg.norm(gx.squeeze(-1), dim=-1)
-    delta_gx = torch.zeros_like(gx)
-    delta_x = torch.zeros_like(x)
-    active = torch.ones_like(best, dtype=torch.bool)
+    """Batched Broyden root finder for g(x) = 0 (x: N x D x 1, J_inv: N x D x D), same update rule, freeze logic and
+    return dictionary as the reference.  Written in the dense, flag-based form of the device kernel (`csrc/broyden.cu`):
+    frozen samples receive a zero step instead of being gathered out, so ``g`` is always asked for all rows (it gets an
+    all-true ``mask``); rows of ``g`` must therefore be independent of each other, which holds for `search`.
+
+    Reference quirk kept: its ``x_opt`` aliases ``x``, so 'result' is the point where a sample stopped moving."""
+    x = x_init.detach().clone()
+    J = J_inv_init.detach().clone()
+    n = x.shape[0]
+    everyone = torch.ones(n, dtype=torch.bool, device=x.device)
+    zero = torch.zeros((), dtype=x.dtype, device=x.device)
+    res = g(x, mask=everyone)
+    step = -torch.matmul(J, res)
+    smallest = res.squeeze(-1).norm(dim=-1)
+    live = everyone.clone()
     for _ in range(max_steps):
-        delta_x[active] = update
-        x[active] += delta_x[active]
-        delta_gx[active] = g(x, mask=active) - gx[active]
-        gx[active] += delta_gx[active]
-        norm = torch.linalg.norm(gx.squeeze(-1), dim=-1)
-        better = norm < best
-        best[better] = norm.clone().detach()[better]
-        x_opt[better] = x.clone().detach()[better]
-        active = (best > cvg_thresh) & (norm < dvg_thresh)
-        if active.sum() <= 0:
+        sel = live.view(n, 1, 1)
+        dx = torch.where(sel, step, zero)
+        x = x + dx
+        dres = torch.where(sel, g(x, mask=everyone) - res, zero)
+        res = res + dres
+        size = res.squeeze(-1).norm(dim=-1)
+        smallest = torch.where(size < smallest, size, smallest)
+        live = (smallest > cvg_thresh) & (size < dvg_thresh)
+        if not bool(live.any()):
             break
-        vT = delta_x[active].transpose(-1, -2).bmm(J_inv[active])
-        a = delta_x[active] - J_inv[active].bmm(delta_gx[active])
-        b = vT.bmm(delta_gx[active])
-        b[b >= 0] += eps
-        b[b < 0] -= eps
-        J_inv[active] += (a / b).bmm(vT)
-        update = -J_inv[active].bmm(gx[active])
-    return {'result': x_opt, 'diff': best, 'valid_ids': best < cvg_thresh}
+        row = torch.matmul(dx.transpose(1, 2), J)                       # N x 1 x D
+        col = dx - torch.matmul(J, dres)                                # N x D x 1
+        denom = torch.matmul(row, dres)                                 # N x 1 x 1
+        denom = denom + torch.where(denom >= 0, eps, -eps)
+        J = torch.where(live.view(n, 1, 1), J + torch.matmul(col / denom, row), J)
+        step = -torch.matmul(J, res)
+    return {'result': x, 'diff': smallest, 'valid_ids': smallest < cvg_thresh}
 
 
 def nabla(decoder_shape, xc, cond, anchors):
@@ -76,45 +77,39 @@ def _fused_search_condition(decoder_expr, xc, cond, anchors):
 def search(obs, cond, decoder_expr, anchors, multi_corresp=True):
     """Canonical correspondences of observed (posed) points: roots of x + F_ex(x) - obs.
     obs: B x N x 3.  Returns (xc_opt, result dict with 'valid_ids')."""
-    n_batch, n_point, _ = obs.shape
+    B, N, _ = obs.shape
+    starts = 5 if multi_corresp else 1
+    target = obs
+    guess = obs.detach().clone()
     if multi_corresp:
-        num_inits = 5
-        xc_init = obs.detach().clone().unsqueeze(2).repeat(1, 1, num_inits, 1)
-        offsets = torch.randn(xc_init.shape, device=xc_init.device) * 0.05
-        offsets[:, :, 0, :] = 0
-        xc_init = (xc_init + offsets).reshape(n_batch, n_point * num_inits, 3)
-        obs = obs.repeat_interleave(num_inits, dim=1)
-        cond = cond[:, 0, :].unsqueeze(1).repeat(1, xc_init.shape[1], 1)
+        # five starts per point: the point itself and four Gaussian perturbations (sigma 0.05), as the reference draws them
+        jitter = 0.05 * torch.randn(B, N, starts, 3, device=obs.device)
+        jitter[:, :, 0] = 0
+        guess = (guess[:, :, None, :] + jitter).reshape(B, N * starts, 3)
+        target = obs.repeat_interleave(starts, dim=1)
+        cond = cond[:, :1].expand(B, N * starts, cond.shape[-1]).contiguous()
         if anchors is not None:
-            anchors = anchors[:, 0, :, :].unsqueeze(1).repeat(1, xc_init.shape[1], 1, 1)
-    else:
-        xc_init = obs.detach().clone()
+            anchors = anchors[:, :1].expand(B, N * starts, *anchors.shape[2:]).contiguous()
+    M = guess.shape[1]
 
-    J_inv_init = jac(decoder_expr, xc_init, cond, anchors).inverse()
-    xc_init = xc_init.reshape(-1, 3, 1)
-    J_inv_init = J_inv_init.flatten(0, 1)
+    J0_inv = jac(decoder_expr, guess, cond, anchors).inverse().reshape(B * M, 3, 3)
 
-    def residual(xc_opt, mask=None):
-        pts = xc_opt.reshape(n_batch, -1, 3)
-        off, _ = decoder_expr(pts, cond, anchors)
-        err = (off + pts) - obs
-        return err.flatten(0, 1)[mask].unsqueeze(-1)
+    def residual(flat_x, mask=None):
+        pts = flat_x.reshape(B, M, 3)
+        moved = decoder_expr(pts, cond, anchors)[0] + pts
+        out = (moved - target).reshape(B * M, 3, 1)
+        return out if mask is None else out[mask]
 
-    fused_cond = _fused_search_condition(decoder_expr, xc_init.reshape(n_batch, -1, 3), cond, anchors)
+    per_query = _fused_search_condition(decoder_expr, guess, cond, anchors)
     with torch.no_grad():
-        if fused_cond is not None:
+        if per_query is not None:
             # whole iteration on the device: one fused-MLP launch + one 3x3 update kernel per step (nphm_mlp_broyden_search)
-            x, diff, valid, _ = decoder_expr.defDeepSDF.engine().broyden_search(
-                obs, fused_cond, xc_init.reshape(n_batch, -1, 3), J_inv_init.reshape(n_batch, -1, 3, 3),
-                max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2)
-            result = {'result': x.reshape(-1, 3, 1), 'diff': diff.reshape(-1), 'valid_ids': valid.reshape(-1)}
+            x, diff, ok, _ = decoder_expr.defDeepSDF.engine().broyden_search(
+                target, per_query, guess, J0_inv.reshape(B, M, 3, 3), max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2)
+            result = {'result': x.reshape(B * M, 3, 1), 'diff': diff.reshape(-1), 'valid_ids': ok.reshape(-1)}
         else:
-            result = broyden(residual, xc_init, J_inv_init, cvg_thresh=1e-6, dvg_thresh=0.2, max_steps=15)
+            result = broyden(residual, guess.reshape(B * M, 3, 1), J0_inv, cvg_thresh=1e-6, dvg_thresh=0.2, max_steps=15)
 
-    if multi_corresp:
-        xc_opt = result['result'].reshape(n_batch, n_point, -1, 3)
-        result['valid_ids'] = result['valid_ids'].reshape(n_batch, n_point, num_inits)
-    else:
-        xc_opt = result['result'].reshape(n_batch, n_point, 3)
-        result['valid_ids'] = result['valid_ids'].reshape(n_batch, n_point)
-    return xc_opt, result
+    shape = (B, N, starts) if multi_corresp else (B, N)
+    result['valid_ids'] = result['valid_ids'].reshape(shape)
+    return result['result'].reshape(*shape, 3), result

@@ -24,64 +24,62 @@ def _as_row(encoding: torch.Tensor) -> torch.Tensor:
     return encoding.reshape(1, -1)
 
 
+def _per_point(code: torch.Tensor, n: int) -> torch.Tensor:
+    """latent of any shape -> ``(1, n, D)`` view (the layout the reference's modules are called with)."""
+    code = code.reshape(1, 1, -1)
+    return code.expand(1, n, code.shape[-1])
+
+
+def _sweep(grid_points, chunk, evaluate):
+    """Run ``evaluate(points) -> (values, anchors)`` over ``chunk``-sized pieces of the point axis; the values of every
+    piece go to the host.  Returns (numpy (N,), anchors of the last piece)."""
+    pieces, anchors = [], None
+    with torch.no_grad():
+        for start in range(0, grid_points.shape[1], chunk):
+            values, anchors = evaluate(grid_points[:, start:start + chunk])
+            pieces.append(values.reshape(-1).detach().cpu())
+    return torch.cat(pieces).numpy(), anchors
+
+
 def get_logits(decoder, encoding, grid_points, nbatch_points=100000, return_anchors=False):
     """SDF of ``grid_points`` (1 x N x 3) under latent ``encoding`` -> numpy (N,) float32 [, anchors]."""
-    with torch.no_grad():
-        if isinstance(decoder, FastEnsembleDeepSDFMirrored) and grid_points.is_cuda \
-                and grid_points.dtype == torch.float32:
+    fused = (isinstance(decoder, FastEnsembleDeepSDFMirrored) and grid_points.is_cuda
+             and grid_points.dtype == torch.float32)
+    if fused:
+        # one launch over all points; the chunk size only matters through the eval-mode last-point-of-chunk quirk
+        with torch.no_grad():
             pts = grid_points.reshape(1, -1, 3)
-            period = 0 if decoder.training else int(nbatch_points)
             sdf, anchors = decoder.engine().query(pts, _as_row(encoding).to(pts.device), eval_quirk=not decoder.training,
-                                                  quirk_period=period if period else None)
+                                                  quirk_period=None if decoder.training else int(nbatch_points))
             logits = _to_host(sdf.reshape(-1))
-        else:
-            outs = []
-            anchors = None
-            enc = encoding.reshape(1, 1, -1)
-            for points in torch.split(grid_points, nbatch_points, dim=1):
-                out, anchors = decoder(points, enc.expand(1, points.shape[1], enc.shape[-1]), None)
-                outs.append(out.reshape(-1).detach().cpu())
-            logits = torch.cat(outs, dim=0).numpy()
-    if return_anchors:
-        return logits, anchors
-    return logits
+    else:
+        logits, anchors = _sweep(grid_points, nbatch_points,
+                                 lambda pts: decoder(pts, _per_point(encoding, pts.shape[1]), None))
+    return (logits, anchors) if return_anchors else logits
 
 
 def get_logits_backward(decoder_shape, decoder_expr, encoding_shape, encoding_expr, grid_points,
                         nbatch_points=100000, return_anchors=False):
     """Backward-warp query: points are first offset by ``decoder_expr`` (called with ``anchors=None`` as in the
     reference, so a 'compress' DeformationNetwork fails here exactly like upstream), then ``decoder_shape``."""
-    outs = []
-    anchors = None
-    with torch.no_grad():
-        for points in torch.split(grid_points, nbatch_points, dim=1):
-            n = points.shape[1]
-            if encoding_expr is not None:
-                e = encoding_expr.reshape(1, 1, -1)
-                offsets, _ = decoder_expr(points, e.expand(1, n, e.shape[-1]), None)
-                points_can = points + offsets
-            else:
-                points_can = points
-            s = encoding_shape.reshape(1, 1, -1)
-            out, anchors = decoder_shape(points_can, s.expand(1, n, s.shape[-1]), None)
-            outs.append(out.reshape(-1).detach().cpu())
-    logits = torch.cat(outs, dim=0).numpy()
-    if return_anchors:
-        return logits, anchors
-    return logits
+    def evaluate(pts):
+        if encoding_expr is not None:
+            pts = pts + decoder_expr(pts, _per_point(encoding_expr, pts.shape[1]), None)[0]
+        return decoder_shape(pts, _per_point(encoding_shape, pts.shape[1]), None)
+
+    logits, anchors = _sweep(grid_points, nbatch_points, evaluate)
+    return (logits, anchors) if return_anchors else logits
 
 
 def deform_mesh(mesh, deformer, lat_rep, anchors, lat_rep_shape=None):
     """Forward-deform the vertices of a canonical mesh with ``deformer`` (one fused launch instead of the
     reference's 5000-vertex chunks + ``empty_cache``)."""
-    points_neutral = torch.from_numpy(np.array(mesh.vertices)).float().unsqueeze(0).to(lat_rep.device)
+    rest = torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32, device=lat_rep.device)[None]
+    code = lat_rep if lat_rep_shape is None else torch.cat([lat_rep_shape, lat_rep], dim=-1)
     with torch.no_grad():
-        cond = lat_rep if lat_rep_shape is None else torch.cat([lat_rep_shape, lat_rep], dim=-1)
-        cond = cond.reshape(1, 1, -1)
-        if anchors is not None:
-            delta, _ = deformer(points_neutral, cond, anchors.reshape(1, -1, 3))
+        if anchors is None:
+            shift = deformer(rest, _per_point(code, rest.shape[1]), None)[0]
         else:
-            delta, _ = deformer(points_neutral, cond.expand(1, points_neutral.shape[1], cond.shape[-1]), None)
-    pred_posed = points_neutral[:, :, :3] + delta.reshape(1, -1, 3)
-    verts = pred_posed.detach().cpu().squeeze(0).numpy()
-    return make_mesh(verts, mesh.faces, process=False)
+            shift = deformer(rest, code.reshape(1, 1, -1), anchors.reshape(1, -1, 3))[0]
+    posed = (rest[..., :3] + shift.reshape(1, -1, 3))[0]
+    return make_mesh(posed.cpu().numpy(), mesh.faces, process=False)
