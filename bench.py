@@ -205,11 +205,15 @@ def main():
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)      # 256 MB > 126 MB L2
     launches = {'n': 0}
 
+    # kernels of this library per step (ncu launch list: profiles/r01_launches_bench256_final.txt): grid axes, anchors, folded
+    # constants, [tensor-core records], ensemble | marching cubes: classify, scan, vertices, triangles
+    per_step_launches = 8 + (1 if args.impl in ('auto', 'tc') else 0)
+
     def step_device():
         """grid SDF (in-kernel grid) + marching cubes, everything resident on the device."""
         eng.query_grid(lat, MINI, MAXI, res, 0, total, quirk_period=CHUNK, out=volume)
         v, t = _native.marching_cubes_device(volume.view(res, res, res), 0.0, negate=True)
-        launches['n'] += 4 + 4          # axes, anchors, cvec, ensemble | classify, scan, vertices, triangles
+        launches['n'] += per_step_launches
         return v, t
 
     def barrier():
@@ -241,7 +245,7 @@ def main():
         kev[i][1].record()
         v, t = _native.marching_cubes_device(volume.view(res, res, res), 0.0, negate=True)
         kev[i][2].record()
-        launches['n'] += 8
+        launches['n'] += per_step_launches
         n_tris = t.shape[0]
         del v, t                        # like the warm-up: the mesh buffers go back to torch's caching allocator (no cudaMalloc
                                         # for a second generation of buffers inside the timed region)

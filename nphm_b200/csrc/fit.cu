@@ -12,8 +12,11 @@
 // Kernels (fp32 FFMA; the step is latency bound: 5 x 1000 points):
 //   fit_member_kernel<fwd>  one CTA per (64-point tile, member): forward, s_k -> global
 //   fit_blend_kernel        per point: blend, |sdf| clamp, kept count / sum
-//   fit_member_kernel<bwd>  forward again with all activations resident in shared memory (199 KB), backward in place,
-//                           per-member delta sums and blend-path anchor gradients -> atomics
+//   fit_member_kernel<bwd>  (configurations without the tensor-core path) forward again with all activations resident in
+//                           shared memory (199 KB), backward in place, per-member delta sums and blend-path anchor
+//                           gradients -> atomics
+//   tensor-core path        forward = tc::ensemble_tc_kernel<.., ACTS> (member outputs + hidden activations to global
+//                           memory), backward = fit_backward_mma_kernel (mma.sync 3xTF32)
 //   fit_member_grad_kernel  per member: delta sums -> g_u, g_c -> latent / anchor gradients
 //   fit_finalize_kernel     mlp_pos forward/backward, regularisers, loss terms, Adam
 #include "engine.cuh"
@@ -26,7 +29,6 @@ namespace fit {
 constexpr int TM = 2;
 constexpr int P = 32 * TM;
 constexpr int kThreads = 512;
-static_assert(TM == 2, "the activation hand-over copies float2 per lane");
 
 struct Dims {
     int n_members, n_symm, n_loc;
@@ -86,26 +88,6 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
     }
     float *rc = sm + (size_t)d.r_c * P, *rh0 = sm + (size_t)d.r_h0 * P, *rh1 = sm + (size_t)d.r_h1 * P;
     float *rh2 = sm + (size_t)d.r_h2 * P, *rh3 = sm + (size_t)d.r_h3 * P, *rs = sm + (size_t)d.r_s * P;
-    if (BWD && b.acts) {
-        // activations h0 | h1 | h2 | h3 were saved by the tensor-core forward pass: copy this tile's 64 columns of every
-        // feature row (256 contiguous bytes each) instead of recomputing the forward pass
-        const int n_feat = 3 * d.H + d.N1;
-        const long long tiles128 = (b.n + 127) / 128;
-        const float *src = b.acts + ((size_t)m * tiles128 + (blockIdx.x >> 1)) * n_feat * 128 + (blockIdx.x & 1) * P;
-        for (int f = warp; f < n_feat; f += nwarps) {
-            const int r = d.r_h0 + f + (f >= d.H + d.N1 ? 3 : 0);     // three skip-input rows sit between h1 and h2
-            const float2 v = *reinterpret_cast<const float2 *>(src + (size_t)f * 128 + lane * TM);
-            *reinterpret_cast<float2 *>(sm + (size_t)r * P + lane * TM) = v;
-        }
-        if (warp == 0) {
-#pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                const long long idx = p0 + lane * TM + i;
-                rs[lane * TM + i] = valid[i] ? b.member_s[idx * d.n_members + m] : 0.f;
-            }
-        }
-        __syncthreads();
-    } else {
     if (warp == 0) {
         float cx[TM], cy[TM], cz[TM];
 #pragma unroll
@@ -134,7 +116,6 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
     __syncthreads();
     narrow_layer<TM>(L[4], L[4].Wt, cv + L[4].coff, rh3, rs, warp, lane, nwarps);
     __syncthreads();
-    }
 
     if (!BWD) {
         if (warp == 0) {

@@ -188,3 +188,30 @@ def test_surface_loss_gradients_wrt_latent_and_points(cuda_device):
     out = _FusedSurfaceLoss.apply(xb, zb, torch.zeros_like(valid), 0.1, dec)
     out.backward()
     assert torch.isnan(out) and float(xb.grad.abs().max()) == 0.0 and float(zb.grad.abs().max()) == 0.0
+
+
+def test_fit_step_on_a_configuration_without_tensor_core_path(cuda_device):
+    """A non-NPHM ensemble shape (hidden 128, condition 16+8) is not taken by the tcgen05 kernel: the fitting step then runs
+    its fp32 FFMA forward/backward kernels.  Their latent gradient must match autograd through the composite module."""
+    from conftest import mean_anchors
+    from nphm_b200.models.EnsembledDeepSDF import FastEnsembleDeepSDFMirrored
+    from nphm_b200.models.fitting import IdentityFitter
+    torch.manual_seed(4)
+    dec = FastEnsembleDeepSDFMirrored(lat_dim_glob=16, lat_dim_loc=8, n_loc=39, n_symm_pairs=16, anchors=mean_anchors(),
+                                      hidden_dim=128, n_layers=4, pos_mlp_dim=64).to(cuda_device).train()
+    dec.anchors = dec.anchors.to(cuda_device)
+    pts = torch.randn(1, 900, 3, device=cuda_device) * 0.15 + torch.tensor([0.0, 0.05, -0.1], device=cuda_device)
+    z = torch.randn(dec.lat_dim, device=cuda_device) * 0.05
+    lam, clamp = 2.0, 0.1
+    za = z.clone().reshape(1, 1, -1).requires_grad_(True)
+    sdf, _ = dec(pts, za, None)
+    l = sdf.abs()
+    ref = lam * l[l < clamp].mean()
+    ref.backward()
+    fitter = IdentityFitter(dec, cuda_device)
+    fitter.latent.copy_(z)
+    fitter.step(pts, {'surface': lam}, clamp, 0.01, apply_update=False)
+    lt = fitter.loss_terms.cpu().numpy()
+    assert int(lt[5]) == int((l < clamp).sum())
+    assert abs(lam * lt[0] - ref.item()) < 1e-5
+    assert _rel(fitter.grad.cpu().numpy(), za.grad.reshape(-1).cpu().numpy()) < 2e-4
