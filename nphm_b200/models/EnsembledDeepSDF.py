@@ -175,6 +175,14 @@ class FastEnsembleDeepSDFMirrored(nn.Module):
             raise ValueError('FastEnsembleDeepSDFMirrored needs mean anchors')
         return a.reshape(self.num_kps, 3).to(device=device, dtype=dtype)
 
+    def predict_anchors(self, lat_rep: torch.Tensor) -> torch.Tensor:
+        """Anchors ``B x n_loc x 3`` of the codes ``lat_rep`` (B x * x lat_dim): ``mlp_pos(z_glob) + mean anchors``.  The same
+        values as the second return of :meth:`forward` (which the reference's fitters obtain by evaluating the whole ensemble
+        on a dummy point), differentiable w.r.t. the code."""
+        z_glob = lat_rep.reshape(lat_rep.shape[0], -1, self.lat_dim)[:, 0, :self.lat_dim_glob]
+        out = self.mlp_pos(z_glob).view(-1, self.num_kps, 3)
+        return out + self.mean_anchors(out.device, out.dtype)[None]
+
     # ------------------------------------------------------------------ forward
     def forward(self,
                 xyz: torch.Tensor,
