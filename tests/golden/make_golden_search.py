@@ -6,7 +6,8 @@
 
 Two observations x 300 points against the seeded deformation network of make_golden.py (seed 10); its output layer is
 scaled by 80 so that the search needs several quasi-Newton steps and ten samples fail to converge (all exit paths
-of the loop are pinned).  Writes search.npz: inputs, the reference's correspondences, residual norms, valid mask."""
+of the loop are pinned), plus the multi-start variant (multi_corresp=True, seed 33) on the first 60 points of each
+observation.  Writes search.npz: inputs, the reference's correspondences, residual norms, valid masks."""
 import os
 import numpy as np
 import torch
@@ -47,9 +48,18 @@ def main():
     diff = res['diff'].numpy()
     print('valid %d / %d, diff quantiles %s, max |xc-obs| %.4f' % (valid.sum(), valid.size,
           np.quantile(diff, [0.1, 0.5, 0.9, 1.0]), float((xc - torch.from_numpy(obs)).abs().max())))
+    # multi-start variant (the function's default): 5 starts per point, perturbations drawn from torch's global generator
+    n_multi = 60
+    torch.manual_seed(33)
+    # (the reference's multi-start residual only supports a batch of one: iterative_root_finding.py:143-146)
+    xc_m, res_m = search(torch.from_numpy(obs[:1, :n_multi]), glob_cond[:1].repeat(1, n_multi, 1), dfn, sa[:1, :n_multi],
+                         multi_corresp=True)
+    print('multi-start: valid %d / %d' % (int(res_m['valid_ids'].sum()), res_m['valid_ids'].numel()))
     np.savez_compressed(os.path.join(G.HERE, 'search.npz'), out_scale=np.float32(OUT_SCALE), latent_id=lat.numpy(),
                         z_ex=z_ex.numpy(), anchors=anc.numpy().reshape(39, 3), obs=obs, xc=xc.detach().numpy(),
-                        diff=diff.reshape(2, n_point), valid=valid.reshape(2, n_point))
+                        diff=diff.reshape(2, n_point), valid=valid.reshape(2, n_point),
+                        multi_seed=np.int64(33), multi_n=np.int64(n_multi), xc_multi=xc_m.detach().numpy(),
+                        valid_multi=res_m['valid_ids'].numpy(), diff_multi=res_m['diff'].numpy())
 
 
 if __name__ == '__main__':

@@ -110,3 +110,27 @@ def test_forward_mode_jacobian_equals_reverse_mode():
         assert dfn.offset_jacobian(xc, cond, anchors) is None     # training-mode noise: reverse mode only
     finally:
         dfn.eval()
+
+
+def test_search_mirror_follows_reference_single_and_multi_start():
+    """The rewritten `search` / `broyden` (dense, flag-based) on CPU against the reference's own runs (search.npz):
+    single start on 2 x 300 points and the multi-start default (5 starts, same torch seed) on 60 points."""
+    import torch
+    from test_oracle import _search_setup
+    from nphm_b200.models.iterative_root_finding import search
+    g, dfn, obs, cond, anchors = _search_setup()
+    n = obs.shape[1]
+    xc, res = search(obs, cond.repeat(1, n, 1), dfn, anchors, multi_corresp=False)
+    valid = res['valid_ids'].numpy()
+    both = valid & g['valid']
+    assert xc.shape == (2, n, 3) and valid.shape == (2, n)
+    assert (valid == g['valid']).mean() >= 0.97
+    assert np.abs(xc.detach().numpy()[both] - g['xc'][both]).max() < 5e-5
+    m = int(g['multi_n'])
+    torch.manual_seed(int(g['multi_seed']))
+    xm, rm = search(obs[:1, :m], cond[:1].repeat(1, m, 1), dfn, anchors[:1, :m], multi_corresp=True)
+    vm = rm['valid_ids'].numpy()
+    assert xm.shape == (1, m, 5, 3) and vm.shape == (1, m, 5)
+    assert (vm == g['valid_multi']).mean() >= 0.97
+    bothm = vm & g['valid_multi']
+    assert np.abs(xm.detach().numpy()[bothm] - g['xc_multi'][bothm]).max() < 5e-5
