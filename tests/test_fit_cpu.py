@@ -134,3 +134,27 @@ def test_search_mirror_follows_reference_single_and_multi_start():
     assert (vm == g['valid_multi']).mean() >= 0.97
     bothm = vm & g['valid_multi']
     assert np.abs(xm.detach().numpy()[bothm] - g['xc_multi'][bothm]).max() < 5e-5
+
+
+def test_surface_loss_gradients_of_the_composite_match_reference_autograd():
+    """Pins the chain  reference autograd -> composite module (here, CPU) -> nphm_fit_surface_grad (GPU test
+    test_surface_loss_gradients_wrt_latent_and_points compares the kernel with this composite):  loss, d loss / d points
+    and d loss / d latent of the joint fitter's surface term against surface_grad.npz (unmodified reference modules)."""
+    import torch
+    from conftest import load_golden, make_ensemble
+    g = load_golden('surface_grad.npz')
+    dec = make_ensemble(0).train()
+    xc, valid = torch.from_numpy(g['points']), torch.from_numpy(g['valid'])
+    for clamp in g['clamps']:
+        tag = '%g' % clamp
+        xa = xc.clone().requires_grad_(True)
+        za = torch.from_numpy(g['latent']).reshape(1, 1, -1).clone().requires_grad_(True)
+        sdf, _ = dec(xa, za.repeat(2, 1, 1), None)
+        l = sdf[valid, :].abs()
+        loss = l[l < float(clamp)].mean()
+        loss.backward()
+        assert int((l < float(clamp)).sum()) == int(g['kept_' + tag])
+        assert abs(loss.item() - float(g['loss_' + tag])) < 1e-6
+        gx, gz = xa.grad.numpy(), za.grad.reshape(-1).numpy()
+        assert np.abs(gx - g['grad_points_' + tag]).max() < 2e-5 * np.abs(g['grad_points_' + tag]).max()
+        assert np.abs(gz - g['grad_latent_' + tag]).max() < 2e-5 * np.abs(g['grad_latent_' + tag]).max()
