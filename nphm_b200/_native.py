@@ -38,6 +38,15 @@ class NativeError(RuntimeError):
     pass
 
 
+# kernels of this library launched per call (ncu launch lists under profiles/); bench.py counts its launches with these
+MC_LAUNCHES = 4                      # classify, scan, vertices, triangles
+
+
+def launches_per_grid_query(impl='auto') -> int:
+    """grid axes, anchors, folded constants, [tensor-core records], ensemble kernel."""
+    return 4 + (1 if impl in ('auto', 'tc', 'tc_pruned') else 0)
+
+
 class EnsembleConfig(Structure):
     _fields_ = [('n_loc', c_int), ('n_symm_pairs', c_int), ('lat_dim_glob', c_int), ('lat_dim_loc', c_int),
                 ('hidden_dim', c_int), ('n_layers', c_int), ('pos_mlp_dim', c_int)]
