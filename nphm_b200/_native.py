@@ -67,6 +67,17 @@ class FitParams(Structure):
                 ('lr', c_float), ('step', c_int)]
 
 
+def stack_supported(n_hidden_layers: int, hidden: int, cond_dim: int) -> bool:
+    """Configurations ``build_stack`` (csrc/api.cu) accepts; anything else takes the composite PyTorch path."""
+    return 2 <= n_hidden_layers <= 10 and hidden > cond_dim + 3
+
+
+def hidden_width(module, n_lin: int) -> int:
+    """Hidden width of a DeepSDF-style stack: the input width of its LAST linear layer (``lin0`` is narrowed to
+    ``hidden - d_in`` when the skip connection sits at layer 1, i.e. for 2 or 3 hidden layers)."""
+    return getattr(module, 'lin%d' % (n_lin - 1)).in_features
+
+
 def impl_code(impl) -> int:
     if isinstance(impl, str):
         return _IMPL_BY_NAME[impl]
@@ -187,7 +198,7 @@ class EnsembleEngine(_Versioned):
         e = module.ensembled_deep_sdf
         n_lin = e.num_layers - 1
         cfg = EnsembleConfig(module.num_kps, module.num_symm_pairs, module.lat_dim_glob, module.lat_dim_loc,
-                             e.lin0.out_features, n_lin - 1, module.pos_mlp_dim)
+                             hidden_width(e, n_lin), n_lin - 1, module.pos_mlp_dim)
         check(lib().nphm_ensemble_create(byref(cfg), byref(self._h)), 'nphm_ensemble_create')
         self.n_lin = n_lin
         self.n_loc = module.num_kps
@@ -222,7 +233,8 @@ class EnsembleEngine(_Versioned):
 
     def refresh(self, module):
         ps = self._params(module)
-        sig = self._signature(ps)
+        anc = module.anchors            # plain attribute (EnsembledDeepSDF.py:192): may be re-assigned after first use
+        sig = self._signature(ps) + ((anc.data_ptr(), anc._version, str(anc.device)) if anc is not None else (None,))
         if sig == self._sig:
             return
         dev = ps[0].device
@@ -291,7 +303,7 @@ class MlpEngine(_Versioned):
     def __init__(self, module):
         self._h = c_void_p()
         self.n_lin = module.num_layers - 1
-        cfg = MlpConfig(module.lat_dim, module.lin0.out_features, self.n_lin - 1, module.out_dim_net)
+        cfg = MlpConfig(module.lat_dim, hidden_width(module, self.n_lin), self.n_lin - 1, module.out_dim_net)
         check(lib().nphm_mlp_create(byref(cfg), byref(self._h)), 'nphm_mlp_create')
         self.out_dim = module.out_dim_net
         self._sig = None

@@ -388,6 +388,8 @@ int make_dims(const nphm_mc_params *p, Dims &d)
 {
     NPHM_REQUIRE(p != nullptr, "nphm_mc: params is NULL");
     NPHM_REQUIRE(p->nx >= 0 && p->ny >= 0 && p->nz >= 0, "nphm_mc: negative dimensions");
+    // a slab that does not start at the global x = 0 plane must bring the cell layer below it (its owner cells)
+    NPHM_REQUIRE(p->x_global0 >= 0 && (p->x_global0 == 0 || p->ghost_lo), "nphm_mc: x_global0 > 0 needs ghost_lo = 1");
     d.nx = p->nx; d.ny = p->ny; d.nz = p->nz;
     d.cx = p->nx - 1; d.cy = p->ny - 1; d.cz = p->nz - 1;
     d.ncells = (d.cx > 0 && d.cy > 0 && d.cz > 0) ? (long long)d.cx * d.cy * d.cz : 0;

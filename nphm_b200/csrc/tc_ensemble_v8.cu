@@ -1,0 +1,553 @@
+// tcgen05 / TMEM kernel for the identity-SDF ensemble, generation "v8": IN-PLACE operand conversion.
+//
+// Reference semantics: FastEnsembleDeepSDFMirrored.forward  src/NPHM/models/EnsembledDeepSDF.py:203-267
+// Same math, same weight slabs, same per-(query, member) records and same warp roles as tc_ensemble.cu (see the header
+// of that file); what changes is where the operands live in TMEM and, with it, how much of the chain overlaps.
+//
+// An fp32 accumulator column holds one value; the fp16 (hi, lo) split of that value needs 2 x 16 bit = one column too.
+// So the epilogue of layer L converts its accumulator D_L into the next layer's A operand IN PLACE: a thread reads the
+// 16 accumulator columns of one k-step (tcgen05.ld.x16), applies bias + softplus, splits, and writes 8 columns of packed
+// hi pairs + 8 columns of packed lo pairs back to the SAME 16 columns.  One 208-column region therefore serves a layer
+// as D and the next one as A, and two regions P, Q (+ a 96-column side buffer S) carry the whole chain:
+//
+//     S [416,512)  A0 k-steps 0-5 of the NEXT member (layer 0 on CUDA cores, computed in the shadow of layer 3's MMAs)
+//     P [0,208)    A0 k-steps 6-12 -> (layer 1 reads S + P) ... D2 -> A2 in place
+//     Q [208,416)  D1 (112 cols) -> A1 in place ... D3
+//
+//     layer 1: A0 (S, P)   -> D1 in Q[0,112)      layer 2: A1 (Q[0,112)) -> D2 in P      layer 3: A2 (P) -> D3 in Q
+//
+// Because D_{L+1} never shares columns with the region that is being converted, the MMAs of EVERY layer start k-step
+// round by k-step round while the previous layer's epilogue is still running (v6 could do that for layer 2 only: D2 + A2 +
+// D3 = 624 > 512 columns forced layer 3 to wait for the complete layer-2 epilogue), and the next member's layer 1 runs
+// while the output layer (dot with w4) of the current member is still being evaluated:
+//
+//   compute warps, member m:   [E3a(m-1): D3 cols 0..111] -> q_lo_free
+//                              E0b(m): A0 k-steps 6-12 -> P            | tensor pipe: layer 1 of m (D1 -> Q[0,112))
+//                              E3b(m-1): D3 cols 112..207, blend       | layer 1 tail
+//                              E1(m): Q[0,112) in place, 2 rounds      | layer 2 (D2 -> P), round by round
+//                              E2(m): P in place, 4 rounds             | layer 3 (D3 -> Q), round by round
+//                              E0a(m+1): A0 k-steps 0-5 -> S           | layer 3 tail
+//
+// Hazards (every reuse is separated by an mbarrier or by the in-order execution of the tensor pipe):
+//   S      written after d_ready(layer 1 of m) proved its last readers (layer-1 k-steps 0-5 of m) complete
+//   P      E0b(m) writes after d_ready(layer 3 of m-1): A2(m-1) is dead.  D2(m) overwrites A0(m): issued after layer 1 of m
+//   Q lo   D1(m) may only be written once every warp has finished E3a(m-1)  -> q_lo_free
+//   Q      D3(m) overwrites A1(m) (issued after layer 2 of m) and Q[112,208), whose last reader E3b(m-1) precedes every
+//          warp's a2_ready arrival
+#include "tc_ensemble.cuh"
+
+namespace nphm {
+namespace tc {
+namespace v8 {
+
+constexpr int kParts = 4;                       // column-unit groups per TMEM lane quarter
+constexpr int kEpiWarps = 4 * kParts;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int kColP = 0, kColQ = 208, kColS = 416;
+constexpr int kU0a = 6;                         // A0 units (k-steps of 16) that live in S
+constexpr int kUnits208 = 13, kUnits112 = 7;
+constexpr int rounds(int units) { return (units + kParts - 1) / kParts; }
+constexpr int kR0b = rounds(kUnits208 - kU0a), kR1 = rounds(kUnits112), kR2 = rounds(kUnits208);
+constexpr int kE3aUnits = 7;                    // D3 columns [0,112) = the columns the next member's D1 needs
+
+struct __align__(128) Smem {
+    uint8_t wbuf[2][kGroupBytes];            // double-buffered weight groups (one bulk copy + one barrier each)
+    float rec[kRecSlots][kRecFloats];
+    float partial[kParts - 1][128];
+    uint64_t w_full[2], w_empty[2];
+    uint64_t rec_full[kRecSlots], rec_empty[kRecSlots];
+    uint64_t a0a_ready, a0b_ready[kR0b], a1_ready[kR1], a2_ready[kR2], q_lo_free, d_ready, mask_ready;
+    unsigned long long maskq[2][4];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
+// one k-step of A operand (16 activations) -> packed fp16 hi pairs in columns [col, col+8), lo pairs in [col+8, col+16)
+__device__ __forceinline__ void store_unit(uint32_t col, const float (&v)[16])
+{
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    tc_st8(col, hi);
+    tc_st8(col + 8, lo);
+}
+
+// accumulator unit + per-column constant from the shared-memory record -> softplus (log2 units)
+__device__ __forceinline__ void load_unit_sp(uint32_t col, const float *bias, float (&v)[16])
+{
+    uint32_t r[16];
+    tc_ld16(col, r);
+    float b[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4 *>(bias + 4 * i);
+        b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+    }
+    tc_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const float t = __uint_as_float(r[e]) + b[e];
+        v[e] = ((NPHM_POLY_MASK >> (e & 7)) & 1) ? sp_t_poly(t) : sp_t(t);
+    }
+}
+
+template <bool PRUNE, bool ACTS>
+__global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tiles_per_query = p.blocked ? p.n_tiles : (p.n_points + 127) / 128;
+    const long long n_tiles = p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+        for (int i = 0; i < kRecSlots; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], kEpiWarps); }
+        mbar_init(&sm.a0a_ready, kEpiWarps);
+        for (int i = 0; i < kR0b; ++i) mbar_init(&sm.a0b_ready[i], kEpiWarps);
+        for (int i = 0; i < kR1; ++i) mbar_init(&sm.a1_ready[i], kEpiWarps);
+        for (int i = 0; i < kR2; ++i) mbar_init(&sm.a2_ready[i], kEpiWarps);
+        mbar_init(&sm.q_lo_free, kEpiWarps);
+        mbar_init(&sm.d_ready, 1);
+        mbar_init(&sm.mask_ready, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == kEpiWarps) {
+        // =========================================================================== producer (bulk async copies)
+        if (lane == 0) {
+            int wb = 0;
+            uint32_t wph = 0, tcount = 0, rcount = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                const int qi = (int)(tile / tiles_per_query);
+                unsigned long long mask = (1ull << p.n_members) - 1;
+                if (PRUNE) {
+                    mbar_wait(&sm.mask_ready, tcount & 1);
+                    const unsigned long long *mq = sm.maskq[tcount & 1];
+                    mask = mq[0] | mq[1] | mq[2] | mq[3];
+                }
+                for (int m = 0; m < p.n_members; ++m) {
+                    if (PRUNE && !((mask >> m) & 1)) continue;
+                    {
+                        const int rslot = rcount % kRecSlots;
+                        mbar_wait(&sm.rec_empty[rslot], ((rcount / kRecSlots) & 1) ^ 1);
+                        mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
+                        bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
+                                 &sm.rec_full[rslot]);
+                        ++rcount;
+                    }
+                    const int set = m < 2 * p.n_symm ? (m >> 1) : m - p.n_symm;
+                    const uint8_t *w = p.weights + (size_t)set * kSetBytes;
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t bytes = g == 0 ? kL1Bytes : (g == 1 ? kL2Bytes : (g == 2 ? 7 * kSlabBytes : 6 * kSlabBytes));
+                        mbar_wait(&sm.w_empty[wb], wph ^ 1);
+                        mbar_expect_tx(&sm.w_full[wb], bytes);
+                        bulk_g2s(sm.wbuf[wb], w, bytes, &sm.w_full[wb]);
+                        w += bytes;
+                        if (++wb == 2) { wb = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // =========================================================================== MMA issuer
+        if (lane == 0) {
+            int wb = 0;
+            uint32_t wph = 0, mph = 0, tcount = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                unsigned long long mask = (1ull << p.n_members) - 1;
+                if (PRUNE) {
+                    mbar_wait(&sm.mask_ready, tcount & 1);
+                    const unsigned long long *mq = sm.maskq[tcount & 1];
+                    mask = mq[0] | mq[1] | mq[2] | mq[3];
+                }
+                for (int m = 0; m < p.n_members; ++m) {
+                    if (PRUNE && !((mask >> m) & 1)) continue;
+                    // one k-step = 3 MMAs (hi*hi + hi*lo + lo*hi) on the in-place operand unit at column `a`
+                    auto kstep = [&](uint32_t d, uint32_t a, uint32_t slab, int n, uint32_t idesc, bool fresh) {
+                        const uint64_t b_hi = make_desc(slab, 128, 256);
+                        const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
+                        tc_mma_ts(d, a, b_hi, idesc, fresh ? 0 : 1);
+                        tc_mma_ts(d, a, b_lo, idesc, 1);
+                        tc_mma_ts(d, a + 8, b_hi, idesc, 1);
+                    };
+                    auto next_buf = [&]() { if (++wb == 2) { wb = 0; wph ^= 1; } };
+                    // ---- layer 1 (N 112): A0 units 0-5 from S (written one member ahead), 6-12 from P; D1 -> Q[0,112)
+                    {
+                        const uint32_t idesc = make_idesc(kNP1);
+                        mbar_wait(&sm.q_lo_free, mph);
+                        mbar_wait(&sm.a0a_ready, mph);
+                        mbar_wait(&sm.w_full[wb], wph);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(sm.wbuf[wb]);
+#pragma unroll 1
+                        for (int j = 0; j < kU0a; ++j)
+                            kstep(tmem + kColQ, tmem + kColS + 16 * j, base + j * kSlab1Bytes, kNP1, idesc, j == 0);
+#pragma unroll 1
+                        for (int r = 0; r < kR0b; ++r) {
+                            mbar_wait(&sm.a0b_ready[r], mph);
+                            tc_fence_after();
+                            const int j1 = min(kU0a + (r + 1) * kParts, kUnits208);
+                            for (int j = kU0a + r * kParts; j < j1; ++j)
+                                kstep(tmem + kColQ, tmem + kColP + 16 * j, base + j * kSlab1Bytes, kNP1, idesc, false);
+                        }
+                        tc_commit(&sm.w_empty[wb]);
+                        tc_commit(&sm.d_ready);
+                        next_buf();
+                    }
+                    // ---- layer 2 (N 208, K 112): A1 in Q[0,112), D2 -> P, round by round behind the layer-1 epilogue
+                    {
+                        const uint32_t idesc = make_idesc(kNP2);
+                        mbar_wait(&sm.w_full[wb], wph);
+                        const uint32_t base = smem_u32(sm.wbuf[wb]);
+#pragma unroll 1
+                        for (int r = 0; r < kR1; ++r) {
+                            mbar_wait(&sm.a1_ready[r], mph);
+                            tc_fence_after();
+                            const int j1 = min((r + 1) * kParts, kUnits112);
+                            for (int j = r * kParts; j < j1; ++j)
+                                kstep(tmem + kColP, tmem + kColQ + 16 * j, base + j * kSlabBytes, kNP2, idesc, j == 0);
+                        }
+                        tc_commit(&sm.w_empty[wb]);
+                        tc_commit(&sm.d_ready);
+                        next_buf();
+                    }
+                    // ---- layer 3 (N 208, K 208): A2 in P, D3 -> Q, round by round behind the layer-2 epilogue; two weight groups
+                    {
+                        const uint32_t idesc = make_idesc(kNP3);
+                        mbar_wait(&sm.w_full[wb], wph);
+                        uint32_t base = smem_u32(sm.wbuf[wb]);
+#pragma unroll 1
+                        for (int r = 0; r < kR2; ++r) {
+                            mbar_wait(&sm.a2_ready[r], mph);
+                            tc_fence_after();
+                            const int j1 = min((r + 1) * kParts, kUnits208);
+                            for (int j = r * kParts; j < j1; ++j) {
+                                if (j == 7) {                       // second weight group (k-steps 7-12)
+                                    tc_commit(&sm.w_empty[wb]);
+                                    next_buf();
+                                    mbar_wait(&sm.w_full[wb], wph);
+                                    tc_fence_after();
+                                    base = smem_u32(sm.wbuf[wb]);
+                                }
+                                kstep(tmem + kColQ, tmem + kColP + 16 * j, base + (j < 7 ? j : j - 7) * kSlabBytes, kNP3, idesc, j == 0);
+                            }
+                        }
+                        tc_commit(&sm.w_empty[wb]);
+                        tc_commit(&sm.d_ready);
+                        next_buf();
+                    }
+                    mph ^= 1;
+                }
+            }
+        }
+    } else {
+        // =========================================================================== compute / epilogue warps
+        // thread = (point row, column-unit group): warp w serves TMEM lanes 32*(w&3).. and units u with u % kParts == w>>2.
+        const int q = warp & 3, part = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
+        uint32_t d_ph = 0, tcount = 0, rcount = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            int qi;
+            long long idx, g;
+            bool valid;
+            float x, y, z;
+            if (p.blocked) {
+                // compact 8 x 4 x 4 block of grid points (z fastest inside the block)
+                qi = 0;
+                const long long tz = tile % p.bz, txy = tile / p.bz;
+                const int ty = (int)(txy % p.by), tx = (int)(txy / p.by);
+                const int ix = p.px0 + tx * 8 + (row >> 4), iy = ty * 4 + ((row >> 2) & 3), iz = (int)tz * 4 + (row & 3);
+                g = ((long long)ix * p.res + iy) * p.res + iz;
+                valid = ix <= p.px1 && iy < p.res && iz < p.res && g >= p.first && g < p.first + p.n_points;
+                idx = g - p.first;
+                const int cx_ = min(ix, p.res - 1), cy_ = min(iy, p.res - 1), cz_ = min(iz, p.res - 1);
+                x = __ldg(p.axes + cx_); y = __ldg(p.axes + p.res + cy_); z = __ldg(p.axes + 2 * p.res + cz_);
+                if (!valid) g = p.first;
+            } else {
+                qi = (int)(tile / tiles_per_query);
+                idx = (tile - (long long)qi * tiles_per_query) * 128 + row;
+                valid = idx < p.n_points;
+                g = p.first + (valid ? idx : 0);
+                if (p.xyz) {
+                    const float *pp = p.xyz + ((size_t)qi * p.n_points + (valid ? idx : 0)) * 3;
+                    x = pp[0]; y = pp[1]; z = pp[2];
+                } else {
+                    const long long rr = (long long)p.res * p.res;
+                    const int ix = (int)(g / rr), iy = (int)((g - ix * rr) / p.res), iz = (int)(g % p.res);
+                    x = __ldg(p.axes + ix); y = __ldg(p.axes + p.res + iy); z = __ldg(p.axes + 2 * p.res + iz);
+                }
+            }
+            const bool quirk = p.quirk_period > 0 && ((g % p.quirk_period) == p.quirk_period - 1 || g == p.total - 1);
+            float num = 0.f, den = 0.f;
+            unsigned long long mask = (1ull << p.n_members) - 1;
+            if (PRUNE) {
+                // blend weights of all members for this thread's point: S = sum_k w_k; a member is needed by the tile if
+                // w_k >= tau * (S + 1e-6) for at least one of its points (dropped mass per point < n_members * tau).
+                if (part == 0) {
+                    const float *anc = p.anchors + (size_t)qi * (p.n_members - 1) * 3;
+                    float S = 0.f;
+                    for (int k = 0; k < p.n_members; ++k) {
+                        float d = -0.2f;
+                        if (k < p.n_members - 1) {
+                            const float dx = __ldg(anc + 3 * k) - x, dy = __ldg(anc + 3 * k + 1) - y, dz = __ldg(anc + 3 * k + 2) - z;
+                            const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                            d = -(nrm * nrm);
+                        }
+                        S += expf(__fdiv_rn(d, 0.01f));
+                    }
+                    den = S;
+                    const float thr = p.prune_tau * (S + 1e-6f);
+                    unsigned long long wm = 0;
+                    for (int k = 0; k < p.n_members; ++k) {
+                        float d = -0.2f;
+                        if (k < p.n_members - 1) {
+                            const float dx = __ldg(anc + 3 * k) - x, dy = __ldg(anc + 3 * k + 1) - y, dz = __ldg(anc + 3 * k + 2) - z;
+                            const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                            d = -(nrm * nrm);
+                        }
+                        const bool need = valid && expf(__fdiv_rn(d, 0.01f)) >= thr;
+                        if (__any_sync(0xffffffffu, need)) wm |= 1ull << k;
+                    }
+                    wm |= 1ull << (p.n_members - 1);      // every tile evaluates >= 1 member: keeps all warps in lock step
+                    if (lane == 0) {
+                        sm.maskq[tcount & 1][q] = wm;
+                        mbar_arrive(&sm.mask_ready);
+                    }
+                }
+                mbar_wait(&sm.mask_ready, tcount & 1);
+                const unsigned long long *mq = sm.maskq[tcount & 1];
+                mask = mq[0] | mq[1] | mq[2] | mq[3];
+            }
+
+            // hidden activations for the fitting backward (h = v / S), feature-major so that a warp store is one 128-byte line
+            auto save_unit = [&](float *ab, int f0, int n_real, const float (&v)[16]) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (e < n_real) ab[(size_t)(f0 + e) * 128 + row] = v[e] * (1.0f / kS);
+            };
+            auto acts_of = [&](int member) -> float * {
+                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query + (tile % tiles_per_query)) * kActFeat * 128 : nullptr;
+            };
+            auto publish = [&](uint64_t *bar) {          // my TMEM stores are visible to the MMA issuer after this
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);
+            };
+            auto member_coords = [&](const float *r, float &ccx, float &ccy, float &ccz) {
+                ccx = x - r[kRecMisc + 1]; ccy = y - r[kRecMisc + 2]; ccz = z - r[kRecMisc + 3];
+                if (r[kRecMisc + 5] != 0.f) ccx = -ccx;          // mirrored member
+                ccx *= kS; ccy *= kS; ccz *= kS;                // coordinates in log2 units
+            };
+            // layer 0 on CUDA cores: one unit (16 outputs) of h0 -> A operand unit at TMEM column `col`
+            auto layer0_unit = [&](const float *r, int u, float ccx, float ccy, float ccz, uint32_t col, float *ab) {
+                const float4 *l0 = reinterpret_cast<const float4 *>(r + kRecL0) + 16 * u;
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float4 w = l0[e];
+                    const float t = fmaf(w.x, ccx, fmaf(w.y, ccy, fmaf(w.z, ccz, w.w)));
+                    v[e] = ((NPHM_POLY_MASK >> (e & 7)) & 1) ? sp_t_poly(t) : sp_t(t);     // rows >= 200 are zero: sp(0) meets zero weights
+                }
+                if (ACTS) save_unit(ab, 16 * u, min(16, kH - 16 * u), v);
+                store_unit(col, v);
+            };
+            auto layer0_a = [&](const float *r, float ccx, float ccy, float ccz, float *ab) {
+#pragma unroll 1
+                for (int u = part; u < kU0a; u += kParts) layer0_unit(r, u, ccx, ccy, ccz, tl + kColS + 16 * u, ab);
+            };
+            // output layer on CUDA cores: units [u0, u1) of D3 -> partial dot with w4
+            auto layer3_dot = [&](const float *r, int u0, int u1, float *ab, float acc) -> float {
+#pragma unroll 1
+                for (int u = u0 + part; u < u1; u += kParts) {
+                    float v[16];
+                    load_unit_sp(tl + kColQ + 16 * u, r + kRecB3 + 16 * u, v);
+                    if (ACTS) save_unit(ab, 2 * kH + kN1 + 16 * u, min(16, kH - 16 * u), v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 w = *reinterpret_cast<const float4 *>(r + kRecW4 + 16 * u + 4 * i);     // w4 pad = 0
+                        acc = fmaf(v[4 * i], w.x, acc); acc = fmaf(v[4 * i + 1], w.y, acc);
+                        acc = fmaf(v[4 * i + 2], w.z, acc); acc = fmaf(v[4 * i + 3], w.w, acc);
+                    }
+                }
+                return acc;
+            };
+            // member output s = w4 . h3 + b4 (reduced over the column-unit groups of this lane quarter) and the anchor blend
+            auto finalize = [&](const float *r, int member, uint32_t rslot, float acc) {
+                if (part != 0) sm.partial[part - 1][row] = acc;
+                tc_fence_before();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kParts) : "memory");   // the warps of this lane quarter
+                tc_fence_after();
+                if (part == 0) {
+                    float s = acc + r[kRecMisc + 0];
+#pragma unroll
+                    for (int i = 0; i < kParts - 1; ++i) s += sm.partial[i][row];
+                    if (p.members_out && valid) p.members_out[((size_t)qi * p.n_points + idx) * p.n_members + member] = s;
+                    float d;
+                    if (r[kRecMisc + 4] != 0.f) {
+                        const float dx = r[kRecMisc + 1] - x, dy = r[kRecMisc + 2] - y, dz = r[kRecMisc + 3] - z;
+                        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz) + 10e-6f;
+                        d = -(nrm * nrm);
+                    } else {
+                        d = -0.2f;
+                    }
+                    const float w = expf(__fdiv_rn(d, 0.01f));
+                    num = fmaf(w, quirk ? 1.0f : s, num);
+                    if (!PRUNE) den += w;
+                }
+                // (sm.partial is written again one member later, behind barriers that need every warp of this quarter)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.rec_empty[rslot]);
+            };
+
+            bool a_done = false, have_prev = false;
+            float acc_prev = 0.f;
+            const float *rec_prev = nullptr;
+            float *ab_prev = nullptr;
+            int m_prev = 0;
+            uint32_t rslot_prev = 0;
+
+            for (int m = 0; m < p.n_members; ++m) {
+                if (!((mask >> m) & 1)) continue;
+                const uint32_t rslot = rcount % kRecSlots;
+                mbar_wait(&sm.rec_full[rslot], (rcount / kRecSlots) & 1);
+                const float *rec = sm.rec[rslot];
+                float cx, cy, cz;
+                member_coords(rec, cx, cy, cz);
+                float *const ab = acts_of(m);
+
+                // ---------------- layer 0 on CUDA cores -> A operand of layer 1 (units 0-5 normally exist already)
+                if (!a_done) {
+                    layer0_a(rec, cx, cy, cz, ab);
+                    publish(&sm.a0a_ready);
+                }
+                if (!have_prev) {                        // first member of the tile: nobody is reading Q[0,112)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.q_lo_free);
+                }
+#pragma unroll 1
+                for (int r = 0; r < kR0b; ++r) {
+                    const int u = kU0a + r * kParts + part;
+                    if (u < kUnits208) layer0_unit(rec, u, cx, cy, cz, tl + kColP + 16 * u, ab);
+                    publish(&sm.a0b_ready[r]);
+                }
+                // ---------------- rest of the previous member's output layer, in the shadow of this member's layer-1 MMAs
+                if (have_prev) {
+                    acc_prev = layer3_dot(rec_prev, kE3aUnits, kUnits208, ab_prev, acc_prev);
+                    finalize(rec_prev, m_prev, rslot_prev, acc_prev);
+                }
+
+                // ---------------- epilogue of layer 1: Q[0,112) in place (K of layer 2 = [h1 (101), c (3), 0...])
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int r = 0; r < kR1; ++r) {
+                    const int u = r * kParts + part;
+                    if (u < kUnits112) {
+                        float v[16];
+                        load_unit_sp(tl + kColQ + 16 * u, rec + kRecB1 + 16 * u, v);
+                        if (u == kUnits112 - 1) {            // features 96..100 | c | zero padding
+                            v[5] = cx; v[6] = cy; v[7] = cz;
+#pragma unroll
+                            for (int e = 8; e < 16; ++e) v[e] = 0.f;
+                        }
+                        if (ACTS) save_unit(ab, kH + 16 * u, min(16, kN1 - 16 * u), v);
+                        store_unit(tl + kColQ + 16 * u, v);
+                    }
+                    publish(&sm.a1_ready[r]);
+                }
+
+                // ---------------- epilogue of layer 2: P in place
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int r = 0; r < kR2; ++r) {
+                    const int u = r * kParts + part;
+                    if (u < kUnits208) {
+                        float v[16];
+                        load_unit_sp(tl + kColP + 16 * u, rec + kRecB2 + 16 * u, v);
+                        if (ACTS) save_unit(ab, kH + kN1 + 16 * u, min(16, kH - 16 * u), v);
+                        store_unit(tl + kColP + 16 * u, v);
+                    }
+                    publish(&sm.a2_ready[r]);
+                }
+
+                // ---------------- in the shadow of the layer-3 MMAs: A0 units 0-5 of the next member of this tile -> S
+                const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
+                a_done = rest != 0;
+                if (a_done) {
+                    const uint32_t nslot = (rcount + 1) % kRecSlots;
+                    mbar_wait(&sm.rec_full[nslot], ((rcount + 1) / kRecSlots) & 1);
+                    const float *nrec = sm.rec[nslot];
+                    float nx, ny, nz;
+                    member_coords(nrec, nx, ny, nz);
+                    layer0_a(nrec, nx, ny, nz, acts_of(m + 1 + (__ffsll((long long)rest) - 1)));
+                    publish(&sm.a0a_ready);
+                }
+
+                // ---------------- output layer, first part: D3 columns [0,112) (the columns the next member's D1 lands in)
+                mbar_wait(&sm.d_ready, d_ph);
+                d_ph ^= 1;
+                tc_fence_after();
+                acc_prev = layer3_dot(rec, 0, kE3aUnits, ab, 0.f);
+                if (a_done) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.q_lo_free);
+                }
+                have_prev = true;
+                rec_prev = rec; ab_prev = ab; m_prev = m; rslot_prev = rslot;
+                ++rcount;
+            }
+            if (have_prev) {                             // last member of the tile
+                acc_prev = layer3_dot(rec_prev, kE3aUnits, kUnits208, ab_prev, acc_prev);
+                finalize(rec_prev, m_prev, rslot_prev, acc_prev);
+            }
+            if (part == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kEpiWarps + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+}  // namespace v8
+
+int launch_ensemble_v8(const Params &p, bool prune, bool acts, int grid_x, cudaStream_t stream)
+{
+    const int smem = (int)sizeof(v8::Smem);
+    auto kern = acts ? v8::ensemble_tc_kernel_v8<false, true>
+                     : (prune ? v8::ensemble_tc_kernel_v8<true, false> : v8::ensemble_tc_kernel_v8<false, false>);
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid_x, v8::kThreads, smem, stream>>>(p);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+}  // namespace tc
+}  // namespace nphm

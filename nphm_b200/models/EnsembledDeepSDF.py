@@ -160,6 +160,10 @@ class FastEnsembleDeepSDFMirrored(nn.Module):
         if torch.is_grad_enabled() and (xyz.requires_grad or lat_rep.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):
             return False             # someone may call backward(): keep the autograd graph
+        e = self.ensembled_deep_sdf
+        n_lin = e.num_layers - 1
+        if not _native.stack_supported(n_lin - 1, _native.hidden_width(e, n_lin), self.lat_dim_glob + self.lat_dim_loc):
+            return False             # depth / width the native stack builder rejects: composite path
         return (xyz.dtype == torch.float32 and self.out_dim == 1 and self.input_dim == 3)
 
     def engine(self) -> "_native.EnsembleEngine":

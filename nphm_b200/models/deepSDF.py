@@ -80,7 +80,9 @@ class DeepSDF(nn.Module):
     def _fused_ok(self, xyz, lat_rep) -> bool:
         if not xyz.is_cuda or self.num_freq_bands is not None or self.beta != 100:
             return False
-        if self.lin0.out_features > self._MAX_FUSED_WIDTH or self.out_dim_net > 8 or self.num_layers < 4:
+        n_lin = self.num_layers - 1
+        hidden = _native.hidden_width(self, n_lin)
+        if hidden > self._MAX_FUSED_WIDTH or self.out_dim_net > 8 or not _native.stack_supported(n_lin - 1, hidden, self.lat_dim):
             return False             # e.g. the NPM baseline (hidden 1024): PyTorch composite path
         if torch.is_grad_enabled() and (xyz.requires_grad or lat_rep.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):

@@ -112,6 +112,82 @@ def test_install_as_nphm_aliases():
         sys.modules.update(saved)
 
 
+def test_install_as_nphm_keeps_the_rest_of_the_reference_importable(tmp_path):
+    """After install_as_nphm() every NPHM.* name the reference's scripts import must still resolve: the seven hot-path
+    modules here, everything else (env_paths, data.*, evaluation.*, models.training / loss_functions / training_corresp,
+    utils.mesh_operations) in the reference checkout on sys.path.  A stand-in checkout with the same module names and
+    the same inter-module imports as /root/reference/src/NPHM is used (the real one needs trimesh, wandb, ...)."""
+    import nphm_b200
+    import sys
+    pkg = tmp_path / 'NPHM'
+    for d in ('', 'data', 'evaluation', 'models', 'utils'):
+        (pkg / d).mkdir(exist_ok=True)
+    (pkg / '__init__.py').write_text('')
+    (pkg / 'data' / '__init__.py').write_text('')
+    (pkg / 'env_paths.py').write_text('ASSETS = "/nowhere/"\n')
+    (pkg / 'data' / 'manager.py').write_text('from NPHM import env_paths\nclass DataManager:\n    root = env_paths.ASSETS\n')
+    (pkg / 'data' / 'face_dataset.py').write_text('from NPHM.data.manager import DataManager\nclass ScannerData:\n    m = DataManager\n')
+    (pkg / 'evaluation' / 'metrics.py').write_text('def eval_pointcloud():\n    return 1\n')
+    (pkg / 'utils' / 'mesh_operations.py').write_text('def cut_trimesh_vertex_mask():\n    return 2\n')
+    # the reference's own (slow) versions of the shadowed modules must NOT win
+    (pkg / 'models' / 'deepSDF.py').write_text('raise ImportError("reference deepSDF imported instead of the mirror")\n')
+    (pkg / 'models' / 'reconstruction.py').write_text('raise ImportError("reference reconstruction imported")\n')
+    (pkg / 'models' / 'loss_functions.py').write_text(
+        'from NPHM.models.diff_operators import gradient\nfrom NPHM.models.iterative_root_finding import search, jac, nabla\n'
+        'def compute_loss():\n    return gradient\ndef compute_loss_corresp_forward():\n    return search\n')
+    (pkg / 'models' / 'training.py').write_text(
+        'from NPHM.models.loss_functions import compute_loss\nfrom NPHM.models.reconstruction import get_logits\n'
+        'from NPHM.utils.reconstruction import create_grid_points_from_bounds, mesh_from_logits\n'
+        'from NPHM import env_paths\nclass TrainerAutoDecoder:\n    fn = staticmethod(get_logits)\n')
+    (pkg / 'models' / 'training_corresp.py').write_text(
+        'from NPHM.models.loss_functions import compute_loss_corresp_forward\nfrom NPHM.models.reconstruction import get_logits, deform_mesh\n'
+        'class TrainerAutoDecoder:\n    fn = staticmethod(deform_mesh)\n')
+    saved = {k: v for k, v in sys.modules.items() if k == 'NPHM' or k.startswith('NPHM.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, str(tmp_path))
+    try:
+        for mode in ('fresh', 'reference imported first'):
+            for k in [k for k in sys.modules if k == 'NPHM' or k.startswith('NPHM.')]:
+                del sys.modules[k]
+            if mode != 'fresh':
+                from NPHM import env_paths as _e          # noqa: F401  (what INTEGRATION.md's one-liner does first)
+                with pytest.raises(RuntimeError):
+                    nphm_b200.install_as_nphm()
+                nphm_b200.install_as_nphm(force=True)
+            else:
+                nphm_b200.install_as_nphm()
+            # scripts/fitting/fitting_pointclouds.py:1-7, scripts/training/train*.py:9-11, scripts/evaluation/eval.py
+            from NPHM import env_paths
+            import NPHM.env_paths as env_paths2
+            from NPHM.data.manager import DataManager
+            from NPHM.data.face_dataset import ScannerData
+            from NPHM.evaluation.metrics import eval_pointcloud
+            from NPHM.utils.mesh_operations import cut_trimesh_vertex_mask
+            from NPHM.models.training import TrainerAutoDecoder
+            from NPHM.models import training_corresp as training
+            from NPHM.models.loss_functions import compute_loss, compute_loss_corresp_forward
+            from NPHM.models.deepSDF import DeepSDF, DeformationNetwork
+            from NPHM.models.EnsembledDeepSDF import FastEnsembleDeepSDFMirrored
+            from NPHM.models.fitting import inference_identity_space, inference_iterative_root_finding_joint
+            from NPHM.models.reconstruction import deform_mesh, get_logits, get_logits_backward
+            from NPHM.utils.reconstruction import create_grid_points_from_bounds, mesh_from_logits
+            from NPHM.models.iterative_root_finding import search, jac, nabla
+            from NPHM.models.diff_operators import gradient
+            import nphm_b200.models.reconstruction as mine
+            import nphm_b200.models.deepSDF as mine_sdf
+            assert env_paths is env_paths2 and env_paths.ASSETS == '/nowhere/' and DataManager.root == '/nowhere/'
+            assert ScannerData.m is DataManager and eval_pointcloud() == 1 and cut_trimesh_vertex_mask() == 2
+            assert get_logits is mine.get_logits and DeepSDF is mine_sdf.DeepSDF
+            assert TrainerAutoDecoder.fn is mine.get_logits and training.TrainerAutoDecoder.fn is mine.deform_mesh
+            assert compute_loss() is gradient and compute_loss_corresp_forward() is search
+    finally:
+        sys.path.remove(str(tmp_path))
+        for k in [k for k in sys.modules if k == 'NPHM' or k.startswith('NPHM.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_library_exports_every_declared_symbol():
     from nphm_b200 import _native
     header = open(os.path.join(ROOT, 'include', 'nphm_b200.h')).read()
@@ -160,5 +236,5 @@ def test_bench_reference_arm_contract(tmp_path):
     assert line['impl'] == 'reference' and line['metric'] == 'sdf_query_points_per_s' and line['unit'] == 'points/s'
     assert line['higher_is_better'] is True and line['value'] > 0 and line['e2e']['value'] == line['value']
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline']['cores'] >= 1
     assert 'workload' in line['config']
