@@ -39,7 +39,7 @@ class NativeError(RuntimeError):
 
 
 # kernels of this library launched per call (ncu launch lists under profiles/); bench.py counts its launches with these
-MC_LAUNCHES = 4                      # classify, scan, vertices, triangles
+MC_LAUNCHES = 3                      # classify rows, scan rows, emit rows
 
 
 def launches_per_grid_query(impl='auto') -> int:

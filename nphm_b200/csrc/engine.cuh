@@ -47,7 +47,7 @@ struct nphm_ensemble {
     // per-call scratch
     nphm::DeviceBuffer anchors, cvec, axes, host_latent, host_volume;
     // tensor-core path (tc_ensemble.cu)
-    nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
+    nphm::DeviceBuffer tc_weights, tc_consts, tc_coff, tc_l2slabs;
     bool tc_ready = false;
     bool tc_prune = false;          // opt-in member pruning (NPHM_IMPL_TC_PRUNED)
     float tc_prune_tau = 1e-8f;

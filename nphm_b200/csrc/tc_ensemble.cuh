@@ -48,6 +48,7 @@ constexpr int kThreads = 32 * (kEpiWarps + 2);
 struct Params {
     const uint8_t *weights;     // [n_sets][kSetBytes]
     const float *recs;          // [n_queries][n_members][kRecFloats]
+    const uint8_t *l2_slabs;    // [n_queries][n_members][kSlabBytes]: last k-step slab of layer 2 with the latent-dependent bias row
     const float *xyz;
     const float *axes;
     int res;

@@ -50,6 +50,15 @@ constexpr int rounds(int units) { return (units + kParts - 1) / kParts; }
 constexpr int kR0b = rounds(kUnits208 - kU0a), kR1 = rounds(kUnits112), kR2 = rounds(kUnits208);
 constexpr int kE3aUnits = 7;                    // D3 columns [0,112) = the columns the next member's D1 needs
 
+// Optional timeline trace (build with -DNPHM_TC_TRACE, tools/build_variant.sh): CTA 0 records clock64() at the phase
+// boundaries of its second tile - [member][event], events 0-15 compute warp 0, 16-31 MMA issuer, 32-47 compute warp 13.
+#ifdef NPHM_TC_TRACE
+__device__ long long g_trace[64][48];
+#define TRACE_EVT(cond, m, id) do { if ((cond) && blockIdx.x == 0 && tcount == 1 && (threadIdx.x & 31) == 0) g_trace[m][id] = clock64(); } while (0)
+#else
+#define TRACE_EVT(cond, m, id) do { } while (0)
+#endif
+
 struct __align__(128) Smem {
     uint8_t wbuf[2][kGroupBytes];            // double-buffered weight groups (one bulk copy + one barrier each)
     float rec[kRecSlots][kRecFloats];
@@ -69,34 +78,84 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
                  : "r"(taddr) : "memory");
 }
 
-// one k-step of A operand (16 activations) -> packed fp16 hi pairs in columns [col, col+8), lo pairs in [col+8, col+16)
-__device__ __forceinline__ void store_unit(uint32_t col, const float (&v)[16])
+// warp-uniform election of one lane (the lane that issues tcgen05.mma / tcgen05.commit)
+__device__ __forceinline__ bool elect_one()
 {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    tc_st8(col, hi);
-    tc_st8(col + 8, lo);
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
-// accumulator unit + per-column constant from the shared-memory record -> softplus (log2 units)
-__device__ __forceinline__ void load_unit_sp(uint32_t col, const float *bias, float (&v)[16])
+// half a k-step of A operand (8 activations, half h of the unit at column `col`): packed fp16 hi pairs go to columns
+// [col + 4h, +4), lo pairs to [col + 8 + 4h, +4)  (unit layout: 8 columns of hi pairs, then 8 columns of lo pairs)
+__device__ __forceinline__ void store_half(uint32_t col, int h, const float (&v)[8])
 {
-    uint32_t r[16];
-    tc_ld16(col, r);
-    float b[16];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 t = *reinterpret_cast<const float4 *>(bias + 4 * i);
-        b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
-    }
-    tc_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const float t = __uint_as_float(r[e]) + b[e];
-        v[e] = ((NPHM_POLY_MASK >> (e & 7)) & 1) ? sp_t_poly(t) : sp_t(t);
-    }
+    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    tc_st4(col + 4 * h, hi);
+    tc_st4(col + 8 + 4 * h, lo);
 }
+
+// softplus in log2 units with lg2(1 + e) on the FMA pipe: e * P5(e), |error| < 2.2e-6 log2 units = 1.5e-8 in SDF units
+// (fp32 evaluation included), i.e. at the round-off level of the activations it produces.  One MUFU (ex2) instead of two.
+__device__ __forceinline__ float sp_t_poly5(float t)
+{
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+    float pl = fmaf(e, -0.02645743577f, 0.1234514468f);
+    pl = fmaf(pl, e, -0.2795380944f);
+    pl = fmaf(pl, e, 0.4582707841f);
+    pl = fmaf(pl, e, -0.7182819141f);
+    pl = fmaf(pl, e, 1.442553145f);
+    return fmaf(pl, e, fmaxf(t, 0.0f));
+}
+// which of 8 consecutive elements take the polynomial (bit set) and which the second MUFU (lg2): balances the MUFU pipe
+// (16 lanes/clk/SM) against the issue slots - measured, see DESIGN.md
+#ifndef NPHM_POLY_MASK_V8
+#define NPHM_POLY_MASK_V8 0xAA
+#endif
+__device__ __forceinline__ float sp_sel(float t, int e)
+{
+#if NPHM_V8_POLY5
+    return ((NPHM_POLY_MASK_V8 >> (e & 7)) & 1) ? sp_t_poly5(t) : sp_t(t);
+#else
+    return ((NPHM_POLY_MASK >> (e & 7)) & 1) ? sp_t_poly(t) : sp_t(t);
+#endif
+}
+
+// half an accumulator unit (already in registers) -> softplus.  The per-column constants (bias, latent-folded input part)
+// are already inside the accumulator: the MMAs add them through the K-padding row of B (A carries 1.0 there).
+__device__ __forceinline__ void half_sp(const uint32_t (&r)[16], int h, float (&v)[8])
+{
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = sp_sel(__uint_as_float(r[8 * h + e]), e);
+}
+
+// unit -> compute-warp group assignment.  A phase covers N consecutive units starting at U0 in rounds of kParts units;
+// in a round, group `part` takes the unit with in-round index (part - OFF) mod kParts.  The offsets are chosen so that the
+// phases a warp runs back to back WITHOUT waiting for the tensor pipe in between add up to the same number of units for
+// every group (a round costs ~900 cycles; with OFF = 0 everywhere a member took 14 rounds, now 12):
+//   E3a (7 units) + E0b (7) + E3b (6) = 5 + 5 + 5 + 5     E1 (7) = 2 rounds     E2 (13) + E0a (6) = 5 + 5 + 5 + 4
+static_assert(kParts == 4, "phase offsets below are worked out for four groups");
+template <int V> struct IC { static constexpr int value = V; };
+#ifndef NPHM_V8_OFFSETS
+#define NPHM_V8_OFFSETS 1
+#endif
+#ifndef NPHM_V8_PREFETCH
+#define NPHM_V8_PREFETCH 0        // measured: keeping the next unit's tcgen05.ld in flight made the kernel 45 % SLOWER
+#endif
+#ifndef NPHM_V8_POLY5
+#define NPHM_V8_POLY5 1
+#endif
+#ifndef NPHM_V8_E0A_EARLY
+#define NPHM_V8_E0A_EARLY 0
+#endif
+#if NPHM_V8_OFFSETS
+constexpr int kOffE3a = 0, kOffE0b = 1, kOffE3b = 3, kOffE1 = 0, kOffE2 = 0, kOffE0a = 1;
+#else
+constexpr int kOffE3a = 0, kOffE0b = 0, kOffE3b = 0, kOffE1 = 0, kOffE2 = 0, kOffE0a = 0;
+#endif
 
 template <bool PRUNE, bool ACTS>
 __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Params p)
@@ -142,15 +201,22 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                     const unsigned long long *mq = sm.maskq[tcount & 1];
                     mask = mq[0] | mq[1] | mq[2] | mq[3];
                 }
+                // records run ONE member ahead of the weights (the compute warps start the next member's layer 0 while the
+                // current member's layer-2 MMAs are still running); the first record of a tile is loaded at its start
+                auto load_rec = [&](int member) {
+                    const int rslot = rcount % kRecSlots;
+                    mbar_wait(&sm.rec_empty[rslot], ((rcount / kRecSlots) & 1) ^ 1);
+                    mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
+                    bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + member) * kRecFloats, kRecFloats * 4,
+                             &sm.rec_full[rslot]);
+                    ++rcount;
+                };
+                load_rec(__ffsll((long long)mask) - 1);
                 for (int m = 0; m < p.n_members; ++m) {
                     if (PRUNE && !((mask >> m) & 1)) continue;
                     {
-                        const int rslot = rcount % kRecSlots;
-                        mbar_wait(&sm.rec_empty[rslot], ((rcount / kRecSlots) & 1) ^ 1);
-                        mbar_expect_tx(&sm.rec_full[rslot], kRecFloats * 4);
-                        bulk_g2s(sm.rec[rslot], p.recs + ((size_t)qi * p.n_members + m) * kRecFloats, kRecFloats * 4,
-                                 &sm.rec_full[rslot]);
-                        ++rcount;
+                        const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
+                        if (rest) load_rec(m + 1 + (__ffsll((long long)rest) - 1));
                     }
                     const int set = m < 2 * p.n_symm ? (m >> 1) : m - p.n_symm;
                     const uint8_t *w = p.weights + (size_t)set * kSetBytes;
@@ -159,7 +225,14 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                         const uint32_t bytes = g == 0 ? kL1Bytes : (g == 1 ? kL2Bytes : (g == 2 ? 7 * kSlabBytes : 6 * kSlabBytes));
                         mbar_wait(&sm.w_empty[wb], wph ^ 1);
                         mbar_expect_tx(&sm.w_full[wb], bytes);
-                        bulk_g2s(sm.wbuf[wb], w, bytes, &sm.w_full[wb]);
+                        if (g == 1) {
+                            // layer 2: the last k-step slab carries this (query, member)'s bias row (l2_slab_kernel)
+                            bulk_g2s(sm.wbuf[wb], w, bytes - kSlabBytes, &sm.w_full[wb]);
+                            bulk_g2s(sm.wbuf[wb] + (bytes - kSlabBytes), p.l2_slabs + ((size_t)qi * p.n_members + m) * kSlabBytes,
+                                     kSlabBytes, &sm.w_full[wb]);
+                        } else {
+                            bulk_g2s(sm.wbuf[wb], w, bytes, &sm.w_full[wb]);
+                        }
                         w += bytes;
                         if (++wb == 2) { wb = 0; wph ^= 1; }
                     }
@@ -168,9 +241,26 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
         }
     } else if (warp == kEpiWarps + 1) {
         // =========================================================================== MMA issuer
-        if (lane == 0) {
+        // The WHOLE warp runs the control flow (waits, loops: warp-uniform, so descriptors live in uniform registers and
+        // the k-step loops unroll to straight-line code); one elected lane issues the tcgen05 instructions.  A `lane == 0`
+        // branch around everything made the compiler wrap every MMA in an ELECT/BRA.U.ANY waterfall and rebuild the
+        // descriptors per k-step (~40 instructions per k-step on a warp that competes with four busy epilogue warps for
+        // issue slots: the issue rate, not the tensor pipe, set the pace of the N = 112 layer).
+        {
+            const bool leader = elect_one();
             int wb = 0;
             uint32_t wph = 0, mph = 0, tcount = 0;
+            const uint32_t idesc1 = make_idesc(kNP1), idesc2 = make_idesc(kNP2);
+            // one k-step = 3 MMAs (hi*hi + hi*lo + lo*hi) on the in-place operand unit at column `a`; `b` = descriptor of
+            // the slab's hi half, its lo half lies n * 32 bytes (n * 2 descriptor units) further
+            auto kstep = [&](uint32_t d, uint32_t a, uint64_t b, int n, uint32_t idesc, bool fresh) {
+                if (leader) {
+                    tc_mma_ts(d, a, b, idesc, fresh ? 0 : 1);
+                    tc_mma_ts(d, a, b + (uint64_t)(n * 2), idesc, 1);
+                    tc_mma_ts(d, a + 8, b, idesc, 1);
+                }
+            };
+            auto commit = [&](uint64_t *bar) { if (leader) tc_commit(bar); };
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 unsigned long long mask = (1ull << p.n_members) - 1;
                 if (PRUNE) {
@@ -180,78 +270,77 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 }
                 for (int m = 0; m < p.n_members; ++m) {
                     if (PRUNE && !((mask >> m) & 1)) continue;
-                    // one k-step = 3 MMAs (hi*hi + hi*lo + lo*hi) on the in-place operand unit at column `a`
-                    auto kstep = [&](uint32_t d, uint32_t a, uint32_t slab, int n, uint32_t idesc, bool fresh) {
-                        const uint64_t b_hi = make_desc(slab, 128, 256);
-                        const uint64_t b_lo = make_desc(slab + n * 32, 128, 256);
-                        tc_mma_ts(d, a, b_hi, idesc, fresh ? 0 : 1);
-                        tc_mma_ts(d, a, b_lo, idesc, 1);
-                        tc_mma_ts(d, a + 8, b_hi, idesc, 1);
-                    };
                     auto next_buf = [&]() { if (++wb == 2) { wb = 0; wph ^= 1; } };
                     // ---- layer 1 (N 112): A0 units 0-5 from S (written one member ahead), 6-12 from P; D1 -> Q[0,112)
                     {
-                        const uint32_t idesc = make_idesc(kNP1);
                         mbar_wait(&sm.q_lo_free, mph);
                         mbar_wait(&sm.a0a_ready, mph);
                         mbar_wait(&sm.w_full[wb], wph);
                         tc_fence_after();
-                        const uint32_t base = smem_u32(sm.wbuf[wb]);
-#pragma unroll 1
+                        TRACE_EVT(true, m, 16);
+                        const uint64_t b0 = make_desc(smem_u32(sm.wbuf[wb]), 128, 256);
+#pragma unroll
                         for (int j = 0; j < kU0a; ++j)
-                            kstep(tmem + kColQ, tmem + kColS + 16 * j, base + j * kSlab1Bytes, kNP1, idesc, j == 0);
-#pragma unroll 1
+                            kstep(tmem + kColQ, tmem + kColS + 16 * j, b0 + (uint64_t)(j * (kSlab1Bytes >> 4)), kNP1, idesc1, j == 0);
+                        TRACE_EVT(true, m, 17);
+#pragma unroll
                         for (int r = 0; r < kR0b; ++r) {
                             mbar_wait(&sm.a0b_ready[r], mph);
                             tc_fence_after();
-                            const int j1 = min(kU0a + (r + 1) * kParts, kUnits208);
-                            for (int j = kU0a + r * kParts; j < j1; ++j)
-                                kstep(tmem + kColQ, tmem + kColP + 16 * j, base + j * kSlab1Bytes, kNP1, idesc, false);
+#pragma unroll
+                            for (int j = kU0a + r * kParts; j < kU0a + (r + 1) * kParts; ++j)
+                                if (j < kUnits208)
+                                    kstep(tmem + kColQ, tmem + kColP + 16 * j, b0 + (uint64_t)(j * (kSlab1Bytes >> 4)), kNP1, idesc1, false);
                         }
-                        tc_commit(&sm.w_empty[wb]);
-                        tc_commit(&sm.d_ready);
+                        commit(&sm.w_empty[wb]);
+                        commit(&sm.d_ready);
+                        TRACE_EVT(true, m, 18);
                         next_buf();
                     }
                     // ---- layer 2 (N 208, K 112): A1 in Q[0,112), D2 -> P, round by round behind the layer-1 epilogue
                     {
-                        const uint32_t idesc = make_idesc(kNP2);
                         mbar_wait(&sm.w_full[wb], wph);
-                        const uint32_t base = smem_u32(sm.wbuf[wb]);
-#pragma unroll 1
+                        const uint64_t b0 = make_desc(smem_u32(sm.wbuf[wb]), 128, 256);
+#pragma unroll
                         for (int r = 0; r < kR1; ++r) {
                             mbar_wait(&sm.a1_ready[r], mph);
                             tc_fence_after();
-                            const int j1 = min((r + 1) * kParts, kUnits112);
-                            for (int j = r * kParts; j < j1; ++j)
-                                kstep(tmem + kColP, tmem + kColQ + 16 * j, base + j * kSlabBytes, kNP2, idesc, j == 0);
+                            TRACE_EVT(true, m, 19 + r);
+#pragma unroll
+                            for (int j = r * kParts; j < (r + 1) * kParts; ++j)
+                                if (j < kUnits112)
+                                    kstep(tmem + kColP, tmem + kColQ + 16 * j, b0 + (uint64_t)(j * (kSlabBytes >> 4)), kNP2, idesc2, j == 0);
                         }
-                        tc_commit(&sm.w_empty[wb]);
-                        tc_commit(&sm.d_ready);
+                        commit(&sm.w_empty[wb]);
+                        commit(&sm.d_ready);
+                        TRACE_EVT(true, m, 22);
                         next_buf();
                     }
                     // ---- layer 3 (N 208, K 208): A2 in P, D3 -> Q, round by round behind the layer-2 epilogue; two weight groups
                     {
-                        const uint32_t idesc = make_idesc(kNP3);
                         mbar_wait(&sm.w_full[wb], wph);
-                        uint32_t base = smem_u32(sm.wbuf[wb]);
-#pragma unroll 1
+                        uint64_t b0 = make_desc(smem_u32(sm.wbuf[wb]), 128, 256);
+#pragma unroll
                         for (int r = 0; r < kR2; ++r) {
                             mbar_wait(&sm.a2_ready[r], mph);
                             tc_fence_after();
-                            const int j1 = min((r + 1) * kParts, kUnits208);
-                            for (int j = r * kParts; j < j1; ++j) {
+                            TRACE_EVT(true, m, 23 + r);
+#pragma unroll
+                            for (int j = r * kParts; j < (r + 1) * kParts; ++j) {
+                                if (j >= kUnits208) continue;
                                 if (j == 7) {                       // second weight group (k-steps 7-12)
-                                    tc_commit(&sm.w_empty[wb]);
+                                    commit(&sm.w_empty[wb]);
                                     next_buf();
                                     mbar_wait(&sm.w_full[wb], wph);
                                     tc_fence_after();
-                                    base = smem_u32(sm.wbuf[wb]);
+                                    b0 = make_desc(smem_u32(sm.wbuf[wb]), 128, 256);
                                 }
-                                kstep(tmem + kColQ, tmem + kColP + 16 * j, base + (j < 7 ? j : j - 7) * kSlabBytes, kNP3, idesc, j == 0);
+                                kstep(tmem + kColQ, tmem + kColP + 16 * j, b0 + (uint64_t)((j < 7 ? j : j - 7) * (kSlabBytes >> 4)), kNP3, idesc2, j == 0);
                             }
                         }
-                        tc_commit(&sm.w_empty[wb]);
-                        tc_commit(&sm.d_ready);
+                        commit(&sm.w_empty[wb]);
+                        commit(&sm.d_ready);
+                        TRACE_EVT(true, m, 28);
                         next_buf();
                     }
                     mph ^= 1;
@@ -339,9 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             }
 
             // hidden activations for the fitting backward (h = v / S), feature-major so that a warp store is one 128-byte line
-            auto save_unit = [&](float *ab, int f0, int n_real, const float (&v)[16]) {
+            auto save_half = [&](float *ab, int f0, int n_real, const float (&v)[8]) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
+                for (int e = 0; e < 8; ++e)
                     if (e < n_real) ab[(size_t)(f0 + e) * 128 + row] = v[e] * (1.0f / kS);
             };
             auto acts_of = [&](int member) -> float * {
@@ -361,34 +450,92 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             // layer 0 on CUDA cores: one unit (16 outputs) of h0 -> A operand unit at TMEM column `col`
             auto layer0_unit = [&](const float *r, int u, float ccx, float ccy, float ccz, uint32_t col, float *ab) {
                 const float4 *l0 = reinterpret_cast<const float4 *>(r + kRecL0) + 16 * u;
-                float v[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float4 w = l0[e];
-                    const float t = fmaf(w.x, ccx, fmaf(w.y, ccy, fmaf(w.z, ccz, w.w)));
-                    v[e] = ((NPHM_POLY_MASK >> (e & 7)) & 1) ? sp_t_poly(t) : sp_t(t);     // rows >= 200 are zero: sp(0) meets zero weights
-                }
-                if (ACTS) save_unit(ab, 16 * u, min(16, kH - 16 * u), v);
-                store_unit(col, v);
-            };
-            auto layer0_a = [&](const float *r, float ccx, float ccy, float ccz, float *ab) {
-#pragma unroll 1
-                for (int u = part; u < kU0a; u += kParts) layer0_unit(r, u, ccx, ccy, ccz, tl + kColS + 16 * u, ab);
-            };
-            // output layer on CUDA cores: units [u0, u1) of D3 -> partial dot with w4
-            auto layer3_dot = [&](const float *r, int u0, int u1, float *ab, float acc) -> float {
-#pragma unroll 1
-                for (int u = u0 + part; u < u1; u += kParts) {
-                    float v[16];
-                    load_unit_sp(tl + kColQ + 16 * u, r + kRecB3 + 16 * u, v);
-                    if (ACTS) save_unit(ab, 2 * kH + kN1 + 16 * u, min(16, kH - 16 * u), v);
+                for (int h = 0; h < 2; ++h) {
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (h == 1 && u == kUnits208 - 1) v[0] = 1.0f;      // k = 200: bias row of layer 1; 201..207: zero weight rows
+                    else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 w = *reinterpret_cast<const float4 *>(r + kRecW4 + 16 * u + 4 * i);     // w4 pad = 0
-                        acc = fmaf(v[4 * i], w.x, acc); acc = fmaf(v[4 * i + 1], w.y, acc);
-                        acc = fmaf(v[4 * i + 2], w.z, acc); acc = fmaf(v[4 * i + 3], w.w, acc);
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 w = l0[8 * h + e];
+                            const float t = fmaf(w.x, ccx, fmaf(w.y, ccy, fmaf(w.z, ccz, w.w)));
+                            v[e] = sp_sel(t, e);
+                        }
                     }
+                    if (ACTS) save_half(ab, 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+                    store_half(col, h, v);
                 }
+            };
+            // a phase of layer 0: units [U0, U0 + N) -> region (S for units 0-5, P for the rest), one publish per round
+            auto layer0_phase = [&](auto tU0, auto tN, auto tOff, const float *r, float ccx, float ccy, float ccz, uint32_t region,
+                                    float *ab, uint64_t *bars) {
+                constexpr int U0 = decltype(tU0)::value, N = decltype(tN)::value, OFF = decltype(tOff)::value;
+                constexpr int R = (N + kParts - 1) / kParts;
+                const int i = (part + kParts - OFF) % kParts;
+#pragma unroll 1
+                for (int rr = 0; rr < R; ++rr) {
+                    const int k = rr * kParts + i;
+                    if (k < N) layer0_unit(r, U0 + k, ccx, ccy, ccz, tl + region + 16 * (U0 + k), ab);
+                    if (bars != nullptr) publish(&bars[rr]);
+                }
+            };
+            // a phase over accumulator units [U0, U0 + N) of `region`: the tcgen05.ld of the NEXT unit is in flight while the
+            // current one is converted (two register buffers, the round loop is unrolled); body(u, v) gets the activations
+            // (tPad = the unit whose second half is zero padding: features 200..207 / the c + padding tail of layer 1 - no MUFU
+            //  work is spent there, body() gets zeros)
+            auto tmem_phase = [&](auto tU0, auto tN, auto tOff, auto tPad, uint32_t region, uint64_t *bars, auto &&body) {
+                constexpr int U0 = decltype(tU0)::value, N = decltype(tN)::value, OFF = decltype(tOff)::value, PAD = decltype(tPad)::value;
+                constexpr int R = (N + kParts - 1) / kParts;
+                const int i = (part + kParts - OFF) % kParts;
+#if NPHM_V8_PREFETCH
+                uint32_t buf[2][16];
+                if (i < N) tc_ld16(tl + region + 16 * (U0 + i), buf[0]);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const int k = rr * kParts + i;
+                    if (k < N) {
+                        tc_wait_ld();
+                        if (rr + 1 < R && k + kParts < N) tc_ld16(tl + region + 16 * (U0 + k + kParts), buf[(rr + 1) & 1]);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            if (!(h == 1 && U0 + k == PAD)) half_sp(buf[rr & 1], h, v);
+                            body(U0 + k, h, v);
+                        }
+                    }
+                    if (bars != nullptr) publish(&bars[rr]);
+                }
+#else
+#pragma unroll 1
+                for (int rr = 0; rr < R; ++rr) {
+                    const int k = rr * kParts + i;
+                    if (k < N) {
+                        uint32_t buf[16];
+                        tc_ld16(tl + region + 16 * (U0 + k), buf);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            if (!(h == 1 && U0 + k == PAD)) half_sp(buf, h, v);
+                            body(U0 + k, h, v);
+                        }
+                    }
+                    if (bars != nullptr) publish(&bars[rr]);
+                }
+#endif
+            };
+            // output layer on CUDA cores: a phase of D3 units -> partial dot with w4
+            auto layer3_dot = [&](auto tU0, auto tN, auto tOff, const float *r, float *ab, float acc) -> float {
+                tmem_phase(tU0, tN, tOff, IC<kUnits208 - 1>(), kColQ, nullptr, [&](int u, int h, const float (&v)[8]) {
+                    if (u == kUnits208 - 1 && h == 1) return;          // padding: w4 is zero there
+                    if (ACTS) save_half(ab, 2 * kH + kN1 + 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+#pragma unroll
+                    for (int i4 = 0; i4 < 2; ++i4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(r + kRecW4 + 16 * u + 8 * h + 4 * i4);     // w4 pad = 0
+                        acc = fmaf(v[4 * i4], w.x, acc); acc = fmaf(v[4 * i4 + 1], w.y, acc);
+                        acc = fmaf(v[4 * i4 + 2], w.z, acc); acc = fmaf(v[4 * i4 + 3], w.w, acc);
+                    }
+                });
                 return acc;
             };
             // member output s = w4 . h3 + b4 (reduced over the column-unit groups of this lane quarter) and the anchor blend
@@ -434,94 +581,94 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 float cx, cy, cz;
                 member_coords(rec, cx, cy, cz);
                 float *const ab = acts_of(m);
+                const int tr0 = warp == 0 ? 0 : 32;
+                const bool trw = warp == 0 || warp == 13;
+                TRACE_EVT(trw, m, tr0 + 0);
 
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1 (units 0-5 normally exist already)
                 if (!a_done) {
-                    layer0_a(rec, cx, cy, cz, ab);
+                    layer0_phase(IC<0>(), IC<kU0a>(), IC<kOffE0a>(), rec, cx, cy, cz, kColS, ab, nullptr);
                     publish(&sm.a0a_ready);
                 }
                 if (!have_prev) {                        // first member of the tile: nobody is reading Q[0,112)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.q_lo_free);
                 }
-#pragma unroll 1
-                for (int r = 0; r < kR0b; ++r) {
-                    const int u = kU0a + r * kParts + part;
-                    if (u < kUnits208) layer0_unit(rec, u, cx, cy, cz, tl + kColP + 16 * u, ab);
-                    publish(&sm.a0b_ready[r]);
-                }
+                layer0_phase(IC<kU0a>(), IC<kUnits208 - kU0a>(), IC<kOffE0b>(), rec, cx, cy, cz, kColP, ab, sm.a0b_ready);
+                TRACE_EVT(trw, m, tr0 + 1);
                 // ---------------- rest of the previous member's output layer, in the shadow of this member's layer-1 MMAs
                 if (have_prev) {
-                    acc_prev = layer3_dot(rec_prev, kE3aUnits, kUnits208, ab_prev, acc_prev);
+                    acc_prev = layer3_dot(IC<kE3aUnits>(), IC<kUnits208 - kE3aUnits>(), IC<kOffE3b>(), rec_prev, ab_prev, acc_prev);
                     finalize(rec_prev, m_prev, rslot_prev, acc_prev);
                 }
+                TRACE_EVT(trw, m, tr0 + 2);
 
                 // ---------------- epilogue of layer 1: Q[0,112) in place (K of layer 2 = [h1 (101), c (3), 0...])
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
-#pragma unroll 1
-                for (int r = 0; r < kR1; ++r) {
-                    const int u = r * kParts + part;
-                    if (u < kUnits112) {
-                        float v[16];
-                        load_unit_sp(tl + kColQ + 16 * u, rec + kRecB1 + 16 * u, v);
-                        if (u == kUnits112 - 1) {            // features 96..100 | c | zero padding
-                            v[5] = cx; v[6] = cy; v[7] = cz;
-#pragma unroll
-                            for (int e = 8; e < 16; ++e) v[e] = 0.f;
-                        }
-                        if (ACTS) save_unit(ab, kH + 16 * u, min(16, kN1 - 16 * u), v);
-                        store_unit(tl + kColQ + 16 * u, v);
+                TRACE_EVT(trw, m, tr0 + 3);
+                tmem_phase(IC<0>(), IC<kUnits112>(), IC<kOffE1>(), IC<kUnits112 - 1>(), kColQ, sm.a1_ready, [&](int u, int h, float (&v)[8]) {
+                    if (u == kUnits112 - 1) {                // features 96..100 | c || 1.0 (bias row of layer 2) | zeros
+                        if (h == 0) { v[5] = cx; v[6] = cy; v[7] = cz; }
+                        else v[0] = 1.0f;
                     }
-                    publish(&sm.a1_ready[r]);
-                }
+                    if (ACTS) save_half(ab, kH + 16 * u + 8 * h, kN1 - 16 * u - 8 * h, v);
+                    store_half(tl + kColQ + 16 * u, h, v);
+                });
+                TRACE_EVT(trw, m, tr0 + 4);
+
+                // ---------------- A0 units 0-5 of the next member of this tile -> S (last read by this member's layer 1, which is
+                // complete), placed in the shadow of the layer-2 MMAs (NPHM_V8_E0A_EARLY, their last round cannot start
+                // before the layer-1 epilogue is complete) or of the layer-3 MMAs
+                const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
+                a_done = rest != 0;
+                auto next_layer0_a = [&]() {
+                    if (a_done) {
+                        const uint32_t nslot = (rcount + 1) % kRecSlots;
+                        mbar_wait(&sm.rec_full[nslot], ((rcount + 1) / kRecSlots) & 1);
+                        const float *nrec = sm.rec[nslot];
+                        float nx, ny, nz;
+                        member_coords(nrec, nx, ny, nz);
+                        layer0_phase(IC<0>(), IC<kU0a>(), IC<kOffE0a>(), nrec, nx, ny, nz, kColS,
+                                     acts_of(m + 1 + (__ffsll((long long)rest) - 1)), nullptr);
+                        publish(&sm.a0a_ready);
+                    }
+                };
+                if (NPHM_V8_E0A_EARLY) next_layer0_a();
+                TRACE_EVT(trw, m, tr0 + 10);
 
                 // ---------------- epilogue of layer 2: P in place
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
-#pragma unroll 1
-                for (int r = 0; r < kR2; ++r) {
-                    const int u = r * kParts + part;
-                    if (u < kUnits208) {
-                        float v[16];
-                        load_unit_sp(tl + kColP + 16 * u, rec + kRecB2 + 16 * u, v);
-                        if (ACTS) save_unit(ab, kH + kN1 + 16 * u, min(16, kH - 16 * u), v);
-                        store_unit(tl + kColP + 16 * u, v);
-                    }
-                    publish(&sm.a2_ready[r]);
-                }
-
-                // ---------------- in the shadow of the layer-3 MMAs: A0 units 0-5 of the next member of this tile -> S
-                const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
-                a_done = rest != 0;
-                if (a_done) {
-                    const uint32_t nslot = (rcount + 1) % kRecSlots;
-                    mbar_wait(&sm.rec_full[nslot], ((rcount + 1) / kRecSlots) & 1);
-                    const float *nrec = sm.rec[nslot];
-                    float nx, ny, nz;
-                    member_coords(nrec, nx, ny, nz);
-                    layer0_a(nrec, nx, ny, nz, acts_of(m + 1 + (__ffsll((long long)rest) - 1)));
-                    publish(&sm.a0a_ready);
-                }
-
+                TRACE_EVT(trw, m, tr0 + 5);
+                tmem_phase(IC<0>(), IC<kUnits208>(), IC<kOffE2>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready, [&](int u, int h, float (&v)[8]) {
+                    if (u == kUnits208 - 1 && h == 1) v[0] = 1.0f;          // k = 200: bias row of layer 3
+                    if (ACTS) save_half(ab, kH + kN1 + 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+                    store_half(tl + kColP + 16 * u, h, v);
+                });
+                TRACE_EVT(trw, m, tr0 + 6);
+                if (!NPHM_V8_E0A_EARLY) next_layer0_a();
+                TRACE_EVT(trw, m, tr0 + 7);
                 // ---------------- output layer, first part: D3 columns [0,112) (the columns the next member's D1 lands in)
                 mbar_wait(&sm.d_ready, d_ph);
                 d_ph ^= 1;
                 tc_fence_after();
-                acc_prev = layer3_dot(rec, 0, kE3aUnits, ab, 0.f);
+                TRACE_EVT(trw, m, tr0 + 8);
+                acc_prev = layer3_dot(IC<0>(), IC<kE3aUnits>(), IC<kOffE3a>(), rec, ab, 0.f);
                 if (a_done) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.q_lo_free);
                 }
+                TRACE_EVT(trw, m, tr0 + 9);
                 have_prev = true;
                 rec_prev = rec; ab_prev = ab; m_prev = m; rslot_prev = rslot;
                 ++rcount;
             }
             if (have_prev) {                             // last member of the tile
-                acc_prev = layer3_dot(rec_prev, kE3aUnits, kUnits208, ab_prev, acc_prev);
+                acc_prev = layer3_dot(IC<kE3aUnits>(), IC<kUnits208 - kE3aUnits>(), IC<kOffE3b>(), rec_prev, ab_prev, acc_prev);
                 finalize(rec_prev, m_prev, rslot_prev, acc_prev);
             }
             if (part == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
@@ -537,6 +684,18 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
 }
 
 }  // namespace v8
+
+#ifdef NPHM_TC_TRACE
+}}
+extern "C" int nphm_debug_tc_trace(long long *host, int n_ll)
+{
+    using namespace nphm;
+    NPHM_CUDA_CHECK(cudaDeviceSynchronize());
+    NPHM_CUDA_CHECK(cudaMemcpyFromSymbol(host, tc::v8::g_trace, (size_t)n_ll * 8));
+    return NPHM_OK;
+}
+namespace nphm { namespace tc {
+#endif
 
 int launch_ensemble_v8(const Params &p, bool prune, bool acts, int grid_x, cudaStream_t stream)
 {
