@@ -204,6 +204,16 @@ int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, long long n
                           const unsigned char *mask_dev, float clamp, float *loss_terms_dev,
                           float *grad_latent_dev, float *grad_points_dev, void *workspace_dev, void *stream);
 
+/* Second half of a fitting iteration (regularisers of fitting.py:252-268 + torch.optim.Adam, :278-279) for a surface
+ * gradient that was evaluated elsewhere: the point-sharded fit of one head over several GPUs (north_star / SURVEY.md 8e)
+ * evaluates nphm_fit_surface_grad on every rank's share of the sampled points, combines [n_r * grad_r, n_r * loss_r, n_r]
+ * with ONE all-reduce and then calls this on every rank with the identical global result.
+ * surface_grad_dev: d(mean |sdf| over the kept points)/d latent (lat_dim, un-weighted: lambda_surface is applied here);
+ * surface_stats_dev: [n_kept, sum |sdf| over the kept points]; loss_terms_dev as in nphm_fit_identity_step (may be NULL). */
+int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, float *adam_m_dev, float *adam_v_dev,
+                            const nphm_fit_params *fp, const float *surface_grad_dev, const float *surface_stats_dev,
+                            float *loss_terms_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     'nphm_ensemble_query', 'nphm_ensemble_query_grid', 'nphm_ensemble_get_logits_host',
     'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
-    'nphm_fit_workspace_bytes', 'nphm_fit_identity_step', 'nphm_fit_surface_grad',
+    'nphm_fit_workspace_bytes', 'nphm_fit_identity_step', 'nphm_fit_surface_grad', 'nphm_fit_apply_gradient',
     'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search',
 )
 
@@ -131,6 +131,8 @@ def lib() -> ctypes.CDLL:
                                          POINTER(FitParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.nphm_fit_surface_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
+    L.nphm_fit_apply_gradient.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(FitParams), c_void_p, c_void_p,
+                                          c_void_p, c_void_p]
     L.nphm_broyden_workspace_bytes.argtypes = [c_longlong]
     L.nphm_broyden_workspace_bytes.restype = c_longlong
     L.nphm_mlp_broyden_search.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,

@@ -52,7 +52,7 @@ struct nphm_ensemble {
     bool tc_prune = false;          // opt-in member pruning (NPHM_IMPL_TC_PRUNED)
     float tc_prune_tau = 1e-8f;
     // fitting (fit.cu)
-    nphm::DeviceBuffer fit_scratch;
+    nphm::DeviceBuffer fit_scratch, fit_apply_scratch;
 };
 
 struct nphm_mlp {

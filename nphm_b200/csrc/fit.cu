@@ -748,3 +748,62 @@ extern "C" int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, 
     return fit_step_impl(h, points_dev, n_points, const_cast<float *>(latent_dev), nullptr, nullptr, &fp, 0, loss_terms_dev,
                          grad_latent_dev, mask_dev, grad_points_dev, workspace_dev, stream);
 }
+
+// ------------------------------------------------------------------------------------------------ sharded fitting
+namespace nphm { namespace fit {
+__global__ void load_external_gradient_kernel(const float *__restrict__ g, const float *__restrict__ stats_in, float lambda,
+                                              int n, float *__restrict__ grad, float *__restrict__ stats)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = lambda * g[i];
+    if (i == 0) { stats[0] = stats_in[0]; stats[1] = stats_in[1]; }
+}
+}}
+
+// Second half of a fitting iteration when the surface term was evaluated elsewhere - e.g. on the shards of a point-sharded
+// fit (nphm_b200/distributed.py: every rank calls nphm_fit_surface_grad on its points, ONE all-reduce combines
+// [n_r * grad_r, n_r * loss_r, n_r], then every rank calls this with the identical global mean gradient): adds the
+// regularisers of fitting.py:252-268 and applies the Adam update exactly like nphm_fit_identity_step.
+// surface_grad_dev: d(mean |sdf| over the kept points)/d latent (lat_dim, un-weighted); surface_stats_dev: [n_kept, sum |sdf|].
+extern "C" int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, float *adam_m_dev, float *adam_v_dev,
+                                       const nphm_fit_params *fp, const float *surface_grad_dev, const float *surface_stats_dev,
+                                       float *loss_terms_dev, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(h && h->loaded, "nphm_fit_apply_gradient: weights not loaded");
+    NPHM_REQUIRE(latent_dev && adam_m_dev && adam_v_dev && fp && surface_grad_dev && surface_stats_dev,
+                 "nphm_fit_apply_gradient: NULL argument");
+    fit::Dims d{};
+    d.n_members = h->n_members; d.n_symm = h->cfg.n_symm_pairs; d.n_loc = h->cfg.n_loc;
+    d.H = h->cfg.hidden_dim; d.N1 = h->dims.N[1]; d.C = h->dims.cond_dim; d.G = h->cfg.lat_dim_glob; d.Lc = h->cfg.lat_dim_loc;
+    d.lat_dim = h->lat_dim; d.pos_hid = h->cfg.pos_mlp_dim; d.cvec_stride = h->dims.cvec_stride;
+    fit::Weights w{};
+    for (int i = 0; i < 3; ++i) { w.pos_w[i] = h->pos_w[i].as<float>(); w.pos_b[i] = h->pos_b[i].as<float>(); }
+    w.mean_anchors = h->mean_anchors.as<float>();
+    int rc;
+    const size_t floats = (size_t)d.n_loc * 3 + 8 + d.lat_dim;
+    if ((rc = h->fit_apply_scratch.reserve(floats * sizeof(float)))) return rc;
+    float *p = h->fit_apply_scratch.as<float>();
+    fit::Buffers b{};
+    b.ganch = p; p += d.n_loc * 3;           // zero: the anchor route is already inside surface_grad_dev
+    b.stats = p; p += 8;
+    b.grad = p;
+    NPHM_CUDA_CHECK(cudaMemsetAsync(h->fit_apply_scratch.ptr, 0, floats * sizeof(float), stream));
+    fit::load_external_gradient_kernel<<<(d.lat_dim + 255) / 256, 256, 0, stream>>>(surface_grad_dev, surface_stats_dev,
+                                                                                   fp->lambda_surface, d.lat_dim, b.grad, b.stats);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    fit::FinalizeArgs a{};
+    a.lambda_surface = fp->lambda_surface; a.lambda_reg_global = fp->lambda_reg_global; a.lambda_reg_loc = fp->lambda_reg_loc;
+    a.lambda_reg_unobserved = fp->lambda_reg_unobserved; a.lambda_symm_dist = fp->lambda_symm_dist;
+    const double beta1 = 0.9, beta2 = 0.999;
+    const int step = fp->step > 0 ? fp->step : 1;
+    const double bc1 = 1.0 - std::pow(beta1, step), bc2 = 1.0 - std::pow(beta2, step);
+    a.step_size = (float)((double)fp->lr / bc1);
+    a.bc2_sqrt = (float)std::sqrt(bc2);
+    a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
+    a.eps = 1e-8f; a.apply_update = 1;
+    const size_t fsm = (size_t)(4 * d.pos_hid + 64) * sizeof(float);
+    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, nullptr);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}

@@ -171,3 +171,97 @@ def ensemble_slab_fn(decoder, latent: torch.Tensor, mini, maxi, res: int, nbatch
         return out.view(n_planes, res, res)
 
     return fn
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Point-sharded fitting of ONE head (north_star; SURVEY.md 8e, reference loop src/NPHM/models/fitting.py:197-279)
+# ------------------------------------------------------------------------------------------------------------------
+def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of an n-row batch that `rank` evaluates (contiguous, as even as possible)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def combine_surface_terms(grad: torch.Tensor, loss: torch.Tensor, n_kept: torch.Tensor, group=None):
+    """The ONE collective of a sharded fitting iteration: all-reduce(SUM) of [n_r * grad_r (lat_dim), n_r * loss_r, n_r].
+    Returns (global mean gradient, [n_kept, sum |sdf|]) - identical on every rank.  grad_r / loss_r are this rank's
+    d(mean |sdf|)/d latent and mean |sdf| over ITS kept points (loss_r may be NaN when n_r = 0: it is not used then)."""
+    n = n_kept.reshape(1).to(grad.dtype)
+    payload = torch.cat([grad.reshape(-1) * n, torch.where(n > 0, loss.reshape(1) * n, torch.zeros_like(n)), n])
+    dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+    total = payload[-1]
+    mean_grad = torch.where(total > 0, payload[:-2] / total.clamp(min=1), torch.zeros_like(payload[:-2]))
+    return mean_grad.contiguous(), torch.stack([total, payload[-2]]).contiguous()
+
+
+class _NativeShardOps:
+    """Per-rank surface term + replicated update on the native kernels (nphm_fit_surface_grad / nphm_fit_apply_gradient)."""
+
+    def __init__(self, decoder, device):
+        import ctypes
+        from . import _native
+        self._ct, self._native = ctypes, _native
+        self.device = device
+        self.engine = decoder.engine()
+        self.latent = torch.zeros(decoder.lat_dim, device=device, dtype=torch.float32)
+        self.m = torch.zeros_like(self.latent)
+        self.v = torch.zeros_like(self.latent)
+        self.terms = torch.zeros(8, device=device, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.latent)
+        self.loss_terms = torch.zeros(8, device=device, dtype=torch.float32)
+
+    def surface(self, points: torch.Tensor, clamp: float):
+        pts = points.reshape(-1, 3).to(torch.float32).contiguous()
+        if pts.shape[0] == 0:
+            z = torch.zeros((), device=self.device)
+            return torch.zeros_like(self.latent), z, z
+        nat = self._native
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().nphm_fit_surface_grad(self.engine.handle, pts.data_ptr(), pts.shape[0], self.latent.data_ptr(),
+                                                      None, float(clamp), self.terms.data_ptr(), self.grad.data_ptr(), None, None,
+                                                      torch.cuda.current_stream(self.device).cuda_stream), 'nphm_fit_surface_grad')
+        return self.grad, self.terms[0], self.terms[5]
+
+    def apply(self, mean_grad, stats, lambdas, clamp, lr, step):
+        nat = self._native
+        fp = nat.FitParams(float(lambdas.get('surface', 0.0)), float(lambdas.get('reg_global', 0.0)),
+                           float(lambdas.get('reg_loc', 0.0)), float(lambdas.get('reg_unobserved', 0.0)),
+                           float(lambdas.get('symm_dist', 0.0)), float(clamp), float(lr), int(step))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().nphm_fit_apply_gradient(self.engine.handle, self.latent.data_ptr(), self.m.data_ptr(),
+                                                        self.v.data_ptr(), self._ct.byref(fp), mean_grad.data_ptr(),
+                                                        stats.data_ptr(), self.loss_terms.data_ptr(),
+                                                        torch.cuda.current_stream(self.device).cuda_stream),
+                      'nphm_fit_apply_gradient')
+
+
+def inference_identity_space_sharded(decoder, all_obs, lambdas, n_steps, schedule_cfg, step_scale=1, lr_scale=1, group=None,
+                                     ops=None):
+    """``inference_identity_space`` (reference fitting.py:180-285) for ONE head with the sampled points of every iteration
+    sharded over the ranks of ``group``.  Every rank runs the same loop on the same ``all_obs`` with the same seed, so the
+    CPU-generator sampling stream (fitting.py:214-222) is replicated; the 5 x 1000 sampled points are split row-wise,
+    every rank evaluates the clamped |sdf| term and its latent gradient on its rows, ONE all-reduce
+    (:func:`combine_surface_terms`) makes the global mean gradient, and the regularisers + Adam update are applied
+    identically everywhere - the latent stays bit-identical across ranks without a broadcast.  ``ops`` injects the per-rank
+    kernels (tests use a CPU stand-in).  Returns ``(lat_rep_shape (1,1,D), anchors)`` like the reference."""
+    from .models.fitting import _apply_schedule, _clamp_for_iteration, _sample_observations
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    device = all_obs[0].device
+    if ops is None:
+        ops = _NativeShardOps(decoder, device)
+    lr = 0.01 * lr_scale
+    z_prev = ops.latent.clone()
+    for j in range(int(n_steps * step_scale)):
+        lr = _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr)
+        obs, _ = _sample_observations(all_obs)                       # replicated: same generator state on every rank
+        pts = obs.reshape(-1, 3)
+        lo, hi = shard_rows(pts.shape[0], world, rank)
+        clamp = _clamp_for_iteration(j, step_scale)
+        z_prev.copy_(ops.latent)
+        grad, loss, kept = ops.surface(pts[lo:hi], clamp)
+        mean_grad, stats = combine_surface_terms(grad, loss, kept, group)
+        ops.apply(mean_grad, stats, lambdas, clamp, lr, j + 1)
+    with torch.no_grad():
+        anchors = decoder.predict_anchors(z_prev.reshape(1, 1, -1)) if hasattr(decoder, 'predict_anchors') else None
+    return ops.latent.reshape(1, 1, -1).clone().requires_grad_(True), anchors

@@ -18,6 +18,9 @@ import torch.distributed as dist
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--sharded', action='store_true',
+                    help='ONE head, the sampled points of every iteration sharded over the ranks, one all-reduce per iteration '
+                         '(nphm_b200.distributed.inference_identity_space_sharded) instead of one scan per GPU')
     args = ap.parse_args()
     from conftest import make_ensemble
     from nphm_b200.models.fitting import inference_identity_space
@@ -28,25 +31,39 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     dec = make_ensemble(0, device=dev).train()
-    rng = np.random.RandomState(100 + rank)
+    rng = np.random.RandomState(100 + (0 if args.sharded else rank))
     obs = [torch.from_numpy((rng.randn(2500, 3) * 0.12 + np.array([0.0, 0.05, -0.1])).astype(np.float32)).to(dev) for _ in range(3)]
     lambdas = {'surface': 2.0, 'reg_global': 0.25, 'reg_unobserved': 10, 'reg_loc': 0.05, 'symm_dist': 5.0}
     schedule = {'lr': {200: 2, 400: 2, 600: 2, 800: 2}, 'symm_dist': {200: 10, 500: 9999}, 'reg_glob': {200: 3, 600: 10},
                 'reg_loc': {500: 3, 600: 10}}
-    inference_identity_space(dec, obs, dict(lambdas), n_steps=5, schedule_cfg=schedule)           # warm-up
+    if args.sharded:
+        from nphm_b200.distributed import inference_identity_space_sharded
+        if world == 1:
+            dist.init_process_group('nccl', device_id=dev, init_method='tcp://127.0.0.1:29533', rank=0, world_size=1)
+
+        def fit(n):
+            return inference_identity_space_sharded(dec, obs, dict(lambdas), n_steps=n, schedule_cfg=schedule)
+    else:
+        def fit(n):
+            return inference_identity_space(dec, obs, dict(lambdas), n_steps=n, schedule_cfg=schedule)
+    np.random.seed(0); torch.manual_seed(0)
+    fit(5)                                                                                        # warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     np.random.seed(0); torch.manual_seed(0)
-    z, _ = inference_identity_space(dec, obs, dict(lambdas), n_steps=args.steps, schedule_cfg=schedule)
+    z, _ = fit(args.steps)
     torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({'metric': 'identity_fit', 'n_gpus': world, 'iterations': args.steps, 's_per_scan': dt.item(),
                           'iters_per_s_total': world * args.steps / dt.item(), 'scans_per_hour': world * 3600 / dt.item(),
-                          'finite': bool(torch.isfinite(z).all()), 'scaling': 'replicas (one scan per GPU, no collective)'}))
-    if world > 1:
+                          'finite': bool(torch.isfinite(z).all()),
+                          'scaling': ('strong: one head, points sharded, 1 all-reduce of lat_dim + 2 floats per iteration; '
+                                      'iters_per_s_total / n_gpus = iterations/s of that head') if args.sharded
+                          else 'replicas (one scan per GPU, no collective)'}))
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
