@@ -204,6 +204,35 @@ int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, long long n
                           const unsigned char *mask_dev, float clamp, float *loss_terms_dev,
                           float *grad_latent_dev, float *grad_points_dev, void *workspace_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * DeepSDF-style stacks layer by layer on the generic fp32-accurate tcgen05 linear layer (csrc/tc_linear.cu, mlp_chain.cu).
+ * ---------------------------------------------------------------------------------------------- */
+/* == nphm_mlp_query for ANY width (DeepSDF.forward, reference src/NPHM/models/deepSDF.py:64-89; e.g. the NPM baseline
+ * 515 -> 1024 x 8 of scripts/configs/npm.yaml:2-4, which no fused kernel takes). */
+int nphm_mlp_query_layers(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                          float *out_dev, void *stream);
+/* Value and input Jacobian in one forward-mode pass == `jac` (reference src/NPHM/models/diff_operators.py:26-54: three
+ * autograd passes) without the identity term:  out_dev [q][n][out_dim] (may be NULL), jac_dev [q][n][out_dim][3] = d out / d xyz.
+ * Callers: iterative_root_finding.py:123 (initial inverse Jacobian of the Broyden search), fitting.py:104 (implicit
+ * differentiation of the root). */
+int nphm_mlp_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                      float *out_dev, float *jac_dev, void *stream);
+/* Adjoint pass == what loss.backward() (reference src/NPHM/models/fitting.py:167) propagates through the deformation
+ * network:  grad_cond_dev [q][lat_dim] = sum_n (d out_n / d cond_q)^T grad_out_n  (may be NULL),
+ *           grad_xyz_dev [q][n][3]    = (d out_n / d xyz_n)^T grad_out_n            (may be NULL).   grad_out_dev: [q][n][out_dim]. */
+int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                             const float *grad_out_dev, float *grad_cond_dev, float *grad_xyz_dev, void *stream);
+
+/* Vector-Jacobian product of the ensemble forward w.r.t. its inputs == what torch.autograd computes for
+ * `decoder(xyz, lat)[0].backward(grad_sdf)` on FastEnsembleDeepSDFMirrored in training mode (reference
+ * src/NPHM/models/EnsembledDeepSDF.py:203-267; used by fitting.py:111-167 through loss.backward()):
+ *   grad_points_dev[p] = grad_sdf[p] * d sdf_p / d xyz_p      (n_points * 3, may be NULL)
+ *   grad_latent_dev    = sum_p grad_sdf[p] * d sdf_p / d latent  (lat_dim: member inputs + anchors/mlp_pos + blend weights)
+ * sdf_out_dev (n_points, may be NULL) receives the forward values.  Same workspace as nphm_fit_identity_step. */
+int nphm_ensemble_backward_inputs(nphm_ensemble *h, const float *points_dev, long long n_points, const float *latent_dev,
+                                  const float *grad_sdf_dev, float *sdf_out_dev, float *grad_latent_dev,
+                                  float *grad_points_dev, void *workspace_dev, void *stream);
+
 /* Second half of a fitting iteration (regularisers of fitting.py:252-268 + torch.optim.Adam, :278-279) for a surface
  * gradient that was evaluated elsewhere: the point-sharded fit of one head over several GPUs (north_star / SURVEY.md 8e)
  * evaluates nphm_fit_surface_grad on every rank's share of the sampled points, combines [n_r * grad_r, n_r * loss_r, n_r]

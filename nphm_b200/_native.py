@@ -28,8 +28,10 @@ EXPORTED_SYMBOLS = (
     'nphm_ensemble_create', 'nphm_ensemble_destroy', 'nphm_ensemble_set_prune_threshold', 'nphm_ensemble_load_weights',
     'nphm_ensemble_query', 'nphm_ensemble_query_grid', 'nphm_ensemble_get_logits_host',
     'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
+    'nphm_mlp_query_layers', 'nphm_mlp_jacobian', 'nphm_mlp_backward_inputs',
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
     'nphm_fit_workspace_bytes', 'nphm_fit_identity_step', 'nphm_fit_surface_grad', 'nphm_fit_apply_gradient',
+    'nphm_ensemble_backward_inputs',
     'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search',
 )
 
@@ -118,6 +120,9 @@ def lib() -> ctypes.CDLL:
     L.nphm_mlp_destroy.restype = None
     L.nphm_mlp_load_weights.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_void_p]
     L.nphm_mlp_query.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_void_p]
+    L.nphm_mlp_query_layers.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]
+    L.nphm_mlp_jacobian.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
+    L.nphm_mlp_backward_inputs.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]
     L.nphm_mc_workspace_bytes.argtypes = [POINTER(McParams)]
     L.nphm_mc_workspace_bytes.restype = c_longlong
     L.nphm_mc_count.argtypes = [c_void_p, POINTER(McParams), c_void_p, POINTER(c_longlong), POINTER(c_longlong),
@@ -131,6 +136,8 @@ def lib() -> ctypes.CDLL:
                                          POINTER(FitParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.nphm_fit_surface_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
+    L.nphm_ensemble_backward_inputs.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p]
     L.nphm_fit_apply_gradient.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(FitParams), c_void_p, c_void_p,
                                           c_void_p, c_void_p]
     L.nphm_broyden_workspace_bytes.argtypes = [c_longlong]
@@ -275,6 +282,24 @@ class EnsembleEngine(_Versioned):
                   'nphm_ensemble_query')
         return sdf, anchors
 
+    def backward_inputs(self, xyz: torch.Tensor, latent: torch.Tensor, grad_sdf: torch.Tensor):
+        """Vector-Jacobian product of the training-mode forward (``nphm_ensemble_backward_inputs``): xyz (N,3), latent
+        (lat_dim,), grad_sdf (N,) -> (sdf (N,), d/d latent (lat_dim,), d/d xyz (N,3)) - what autograd gives for
+        ``decoder(xyz, latent)[0].backward(grad_sdf)``, without building a graph."""
+        dev = xyz.device
+        pts = _f32c(xyz).reshape(-1, 3)
+        lat = _f32c(latent).reshape(-1).to(dev)
+        g = _f32c(grad_sdf).reshape(-1)
+        n = pts.shape[0]
+        sdf = torch.empty(n, device=dev, dtype=torch.float32)
+        g_lat = torch.empty(self.lat_dim, device=dev, dtype=torch.float32)
+        g_pts = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_ensemble_backward_inputs(self._h, pts.data_ptr(), n, lat.data_ptr(), g.data_ptr(), sdf.data_ptr(),
+                                                      g_lat.data_ptr(), g_pts.data_ptr(), None, _stream_ptr(dev)),
+                  'nphm_ensemble_backward_inputs')
+        return sdf, g_lat, g_pts
+
     def query_grid(self, latent: torch.Tensor, mini, maxi, res: int, first: int, count: int, quirk_period: int,
                    impl: Optional[int] = None, out: Optional[torch.Tensor] = None):
         """One latent over grid points [first, first+count) of the res^3 grid -> (sdf (count,), anchors)."""
@@ -347,6 +372,45 @@ class MlpEngine(_Versioned):
                                        _mlp_impl(impl), _stream_ptr(dev)),
                   'nphm_mlp_query')
         return out
+
+    def query_layers(self, xyz: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        """Forward, layer by layer on the generic tcgen05 linear layer (any width): xyz B x N x 3, cond B x lat_dim."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        cond = _f32c(cond).to(dev)
+        out = torch.empty(B, N, self.out_dim, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_mlp_query_layers(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(), _stream_ptr(dev)),
+                  'nphm_mlp_query_layers')
+        return out
+
+    def jacobian(self, xyz: torch.Tensor, cond: torch.Tensor):
+        """(out B x N x out_dim, J B x N x out_dim x 3 = d out / d xyz) in one forward-mode pass (nphm_mlp_jacobian)."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        cond = _f32c(cond).to(dev)
+        out = torch.empty(B, N, self.out_dim, device=dev, dtype=torch.float32)
+        J = torch.empty(B, N, self.out_dim, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_mlp_jacobian(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(), J.data_ptr(),
+                                          _stream_ptr(dev)), 'nphm_mlp_jacobian')
+        return out, J
+
+    def backward_inputs(self, xyz: torch.Tensor, cond: torch.Tensor, grad_out: torch.Tensor, want_xyz: bool = False):
+        """Adjoint pass (nphm_mlp_backward_inputs): grad_out B x N x out_dim -> (d/d cond  B x lat_dim, d/d xyz B x N x 3 | None)."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        cond = _f32c(cond).to(dev)
+        g = _f32c(grad_out)
+        g_cond = torch.empty(B, cond.shape[-1], device=dev, dtype=torch.float32)
+        g_xyz = torch.empty(B, N, 3, device=dev, dtype=torch.float32) if want_xyz else None
+        with torch.cuda.device(dev):
+            check(lib().nphm_mlp_backward_inputs(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, g.data_ptr(), g_cond.data_ptr(),
+                                                 _ptr(g_xyz), _stream_ptr(dev)), 'nphm_mlp_backward_inputs')
+        return g_cond, g_xyz
 
     def broyden_search(self, obs: torch.Tensor, cond: torch.Tensor, x_init: torch.Tensor, J_inv_init: torch.Tensor,
                        max_steps: int = 15, cvg_thresh: float = 1e-6, dvg_thresh: float = 0.2, eps: float = 1e-6):

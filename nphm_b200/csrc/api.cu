@@ -297,7 +297,11 @@ extern "C" int nphm_mlp_create(const nphm_mlp_config *cfg, nphm_mlp **out)
     return NPHM_OK;
 }
 
-extern "C" void nphm_mlp_destroy(nphm_mlp *h) { delete h; }
+extern "C" void nphm_mlp_destroy(nphm_mlp *h)
+{
+    if (h) chain_destroy(h);
+    delete h;
+}
 
 extern "C" int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, const float *const *b_dev, void *stream_)
 {
@@ -307,6 +311,10 @@ extern "C" int nphm_mlp_load_weights(nphm_mlp *h, const float *const *w_dev, con
     fill_descriptors(h->dims, h->weights, 1, 0, h->cfg.lat_dim, 0, 0, h->net, h->spec);
     rc = tc_mlp_pack(h, static_cast<cudaStream_t>(stream_));
     if (rc) return rc;
+    if (h->dims.skip >= 1 && h->dims.skip < h->dims.n_lin - 1) {       // stacks the layer chain can run (mlp_chain.cu)
+        rc = chain_pack(h, static_cast<cudaStream_t>(stream_));
+        if (rc) return rc;
+    }
     h->loaded = true;
     return NPHM_OK;
 }

@@ -55,6 +55,8 @@ struct nphm_ensemble {
     nphm::DeviceBuffer fit_scratch, fit_apply_scratch;
 };
 
+namespace nphm { struct MlpChain; }
+
 struct nphm_mlp {
     nphm_mlp_config cfg;
     bool loaded = false;
@@ -66,6 +68,8 @@ struct nphm_mlp {
     // tensor-core path (tc_mlp.cu)
     nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
     bool tc_ready = false;
+    // layer-by-layer tensor-core passes: any width, Jacobian, adjoint (mlp_chain.cu)
+    nphm::MlpChain *chain = nullptr;
 };
 
 namespace nphm {
@@ -79,4 +83,8 @@ bool tc_mlp_supported(const nphm_mlp *h);
 int tc_mlp_pack(nphm_mlp *h, cudaStream_t stream);
 int tc_mlp_launch(nphm_mlp *h, const float *xyz, const float *cvec, int n_queries, long long n_points, float *out,
                   cudaStream_t stream);
+// layer chain (mlp_chain.cu)
+int chain_pack(nphm_mlp *h, cudaStream_t stream);
+void chain_destroy(nphm_mlp *h);
+int mlp_prepare(nphm_mlp *h, const float *cond_dev, int n_queries, cudaStream_t stream);
 }  // namespace nphm

@@ -61,6 +61,9 @@ struct Buffers {
     float *stats;                   // [count, sum |sdf| kept, -, -]
     float *ganch;                   // n_loc x 3
     float *grad;                    // lat_dim
+    const float *upstream;          // optional n: d L / d sdf_p given by the caller (nphm_ensemble_backward_inputs) instead of the
+                                    // clamped-|sdf| loss of the fitters
+    float *sdf_out;                 // optional n: copy of the blended forward output
 };
 
 template <bool BWD>
@@ -441,17 +444,25 @@ __global__ void fit_blend_kernel(const Dims d, const Buffers b, float clamp)
         }
         const float out = __fdiv_rn(num, den + 1e-6f);
         const float l = fabsf(out);
-        const bool kept = l < clamp && (!b.mask || b.mask[idx]);
         b.out[idx] = out; b.S[idx] = den;
-        b.gsign[idx] = kept ? (out > 0.f ? 1.f : (out < 0.f ? -1.f : 0.f)) : 0.f;
-        if (kept) { cnt = 1.f; sum = l; }
+        if (b.sdf_out) b.sdf_out[idx] = out;
+        if (b.upstream) {
+            // plain vector-Jacobian product: the "loss" is sum_p upstream_p * sdf_p (count fixed to 1 so nothing is averaged)
+            b.gsign[idx] = (!b.mask || b.mask[idx]) ? b.upstream[idx] : 0.f;
+            if (idx == 0) cnt = 1.f;
+            sum = b.gsign[idx] * out;
+        } else {
+            const bool kept = l < clamp && (!b.mask || b.mask[idx]);
+            b.gsign[idx] = kept ? (out > 0.f ? 1.f : (out < 0.f ? -1.f : 0.f)) : 0.f;
+            if (kept) { cnt = 1.f; sum = l; }
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
     }
-    if ((threadIdx.x & 31) == 0 && cnt != 0.f) { atomicAdd(b.stats + 0, cnt); atomicAdd(b.stats + 1, sum); }
+    if ((threadIdx.x & 31) == 0 && (cnt != 0.f || sum != 0.f)) { atomicAdd(b.stats + 0, cnt); atomicAdd(b.stats + 1, sum); }
 }
 
 // per member: g_u = W0u^T D0 + W2u^T D2 / sqrt2 ; g_c = W0x^T D0 + W2x^T D2 / sqrt2
@@ -619,7 +630,7 @@ extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long 
 static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
                          float *adam_m_dev, float *adam_v_dev, const nphm_fit_params *fp, int apply_update,
                          float *loss_terms_dev, float *grad_out_dev, const unsigned char *mask_dev, float *grad_points_dev,
-                         void *workspace_dev, void *stream_)
+                         void *workspace_dev, void *stream_, const float *upstream_dev = nullptr, float *sdf_out_dev = nullptr)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NPHM_REQUIRE(h && h->loaded, "nphm_fit_identity_step: weights not loaded");
@@ -672,6 +683,8 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
     float *acts = p;
     b.acts = nullptr;
     b.mask = mask_dev;
+    b.upstream = upstream_dev;
+    b.sdf_out = sdf_out_dev;
     b.grad_points = grad_points_dev;
     if (grad_points_dev) NPHM_CUDA_CHECK(cudaMemsetAsync(grad_points_dev, 0, (size_t)n_points * 3 * sizeof(float), stream));
 
@@ -747,6 +760,25 @@ extern "C" int nphm_fit_surface_grad(nphm_ensemble *h, const float *points_dev, 
     fp.step = 1;
     return fit_step_impl(h, points_dev, n_points, const_cast<float *>(latent_dev), nullptr, nullptr, &fp, 0, loss_terms_dev,
                          grad_latent_dev, mask_dev, grad_points_dev, workspace_dev, stream);
+}
+
+// Vector-Jacobian product of the ensemble forward w.r.t. its inputs (nphm_ensemble_backward_inputs):
+//   grad_points[p]  = grad_sdf[p] * d sdf_p / d xyz_p           (local coordinates of every member + blend weights)
+//   grad_latent     = sum_p grad_sdf[p] * d sdf_p / d latent     (member inputs + anchors/mlp_pos + blend weights)
+// for the training-mode forward (no eval quirk) of FastEnsembleDeepSDFMirrored (EnsembledDeepSDF.py:203-267) - what
+// torch.autograd computes for `decoder(xyz, lat)[0].backward(grad_sdf)`.  Same kernels as the fitting step.
+extern "C" int nphm_ensemble_backward_inputs(nphm_ensemble *h, const float *points_dev, long long n_points, const float *latent_dev,
+                                             const float *grad_sdf_dev, float *sdf_out_dev, float *grad_latent_dev,
+                                             float *grad_points_dev, void *workspace_dev, void *stream)
+{
+    NPHM_REQUIRE(grad_sdf_dev && grad_latent_dev, "nphm_ensemble_backward_inputs: NULL gradient pointer");
+    nphm_fit_params fp{};
+    fp.lambda_surface = 1.0f;
+    fp.clamp = 0.f;
+    fp.lr = 0.f;
+    fp.step = 1;
+    return fit_step_impl(h, points_dev, n_points, const_cast<float *>(latent_dev), nullptr, nullptr, &fp, 0, nullptr,
+                         grad_latent_dev, nullptr, grad_points_dev, workspace_dev, stream, grad_sdf_dev, sdf_out_dev);
 }
 
 // ------------------------------------------------------------------------------------------------ sharded fitting

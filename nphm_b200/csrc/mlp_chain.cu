@@ -1,0 +1,295 @@
+// Layer-by-layer passes of a DeepSDF-style stack on the generic tcgen05 linear layer (tc_linear.cu):
+//
+//   value pass     h_l = softplus(W_l in_l + c_l), s_l = softplus'(.)          (any width: the NPM baseline 515 -> 1024 x 8 ...)
+//   tangent pass   forward-mode derivative w.r.t. xyz:  t_l = s_l * (W_l t_{l-1}),  3 rows per point  ->  Jacobian d out / d xyz
+//   adjoint pass   d_l-1 = s_l-1 * (W_l^T d_l)  ->  gradient w.r.t. the per-query condition (and, optionally, w.r.t. xyz)
+//
+// Reference semantics: DeepSDF.forward src/NPHM/models/deepSDF.py:64-89 (skip connection `cat([x, inp]) / sqrt(2)` at layer
+// nlayers // 2, Softplus(beta = 100)); `jac` src/NPHM/models/diff_operators.py:26-54 (three autograd passes there, one
+// forward-mode pass here); the adjoint pass is what `loss.backward()` (src/NPHM/models/fitting.py:167) does to the deformation
+// network in the joint fitter.  The condition is constant over the points of a query, so its part of layers 0 and `skip` is
+// folded into per-query constants (simt.cu: cvec) and its gradient only needs the per-query column sums of d_0 and d_skip.
+#include "tc_linear.cuh"
+#include <cmath>
+
+namespace nphm {
+namespace chain {
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+
+__global__ void column_sums_kernel(const float *__restrict__ X, int ld, long long rows_per_query, int n_cols, float *__restrict__ out)
+{
+    // out[q][c] = sum over the rows of query q of X[row][c]; grid = (col blocks, queries, row chunks), atomics across chunks
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (c >= n_cols) return;
+    const long long chunk = (rows_per_query + gridDim.z - 1) / gridDim.z;
+    const long long r0 = (long long)blockIdx.z * chunk, r1 = min(rows_per_query, r0 + chunk);
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += X[((size_t)q * rows_per_query + r) * ld + c];
+    if (r1 > r0) atomicAdd(out + (size_t)q * n_cols + c, s);
+}
+
+// grad_cond[q][j] = sum_n W0[n][3 + j] * S0[q][n]  +  sum_n Ws[n][Nh + 3 + j] * Ss[q][n] / sqrt(2)
+__global__ void cond_grad_kernel(const float *__restrict__ W0, int ld0, int N0, const float *__restrict__ S0,
+                                 const float *__restrict__ Ws, int lds, int Ns, int skip_col0, const float *__restrict__ Ss,
+                                 int cond_dim, float *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (j >= cond_dim) return;
+    float s = 0.f;
+    for (int n = 0; n < N0; ++n) s = fmaf(W0[(size_t)n * ld0 + 3 + j], S0[(size_t)q * N0 + n], s);
+    if (Ws) {
+        float t = 0.f;
+        for (int n = 0; n < Ns; ++n) t = fmaf(Ws[(size_t)n * lds + skip_col0 + j], Ss[(size_t)q * Ns + n], t);
+        s = fmaf(t, kInvSqrt2, s);
+    }
+    out[(size_t)q * cond_dim + j] = s;
+}
+
+// out[(q, n)][i][j] = T[(q, n, j)][i]   (tangent rows -> Jacobian layout B x N x out x 3)
+__global__ void jacobian_layout_kernel(const float *__restrict__ T, int ld, long long n_rows, int out_dim, float *__restrict__ J)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * out_dim * 3) return;
+    const int j = (int)(idx % 3);
+    const int i = (int)((idx / 3) % out_dim);
+    const long long n = idx / (3 * out_dim);
+    J[idx] = T[(size_t)(n * 3 + j) * ld + i];
+}
+
+__global__ void add3_kernel(const float *__restrict__ src, int ld, long long rows, float *__restrict__ dst)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * 3) dst[idx] += src[(idx / 3) * ld + idx % 3];
+}
+
+}  // namespace chain
+
+// ------------------------------------------------------------------------------------------------ packed stack
+struct MlpChain {
+    bool packed = false;
+    int n_lin = 0;
+    tcl::PackedLinear fwd[kMaxLayers];        // B = W_l restricted to its point-dependent columns (1/sqrt2 folded at the skip)
+    tcl::PackedLinear adj[kMaxLayers];        // B = W_l^T (input-activation columns only)
+    tcl::PackedLinear adj_x0, adj_xs;         // W_0[:, 0:3]^T and W_skip[:, Nh:Nh+3]^T / sqrt2  (gradient w.r.t. xyz)
+    DeviceBuffer H[kMaxLayers], S[kMaxLayers], T[2], D[2], sums0, sumss, out_tmp;
+    int ld[kMaxLayers];
+};
+
+static int pad4(int n) { return (n + 3) / 4 * 4; }
+
+int chain_pack(nphm_mlp *h, cudaStream_t stream)
+{
+    if (!h->chain) h->chain = new MlpChain();
+    MlpChain &c = *h->chain;
+    const StackDims &s = h->dims;
+    c.n_lin = s.n_lin;
+    int rc;
+    for (int l = 0; l < s.n_lin; ++l) {
+        const float *W = h->weights.W[l].as<float>();
+        const int ldw = s.in_total[l];
+        const float scale = l == s.skip ? chain::kInvSqrt2 : 1.0f;
+        // forward: point-dependent leading columns (xyz | h_{l-1} | [h_{skip-1}, xyz])
+        if ((rc = c.fwd[l].pack(W, ldw, s.N[l], s.K[l], 0, 0, false, scale, stream))) return rc;
+        // adjoint w.r.t. the input activations of layer l (l >= 1): columns [0, N_{l-1})
+        if (l >= 1 && (rc = c.adj[l].pack(W, ldw, s.N[l - 1], s.N[l], 0, 0, true, scale, stream))) return rc;
+        c.ld[l] = pad4(s.N[l]);
+    }
+    if ((rc = c.adj_x0.pack(h->weights.W[0].as<float>(), s.in_total[0], 3, s.N[0], 0, 0, true, 1.0f, stream))) return rc;
+    if (s.skip > 0 && s.skip < s.n_lin &&
+        (rc = c.adj_xs.pack(h->weights.W[s.skip].as<float>(), s.in_total[s.skip], 3, s.N[s.skip], s.N[s.skip - 1], 0, true,
+                            chain::kInvSqrt2, stream))) return rc;
+    c.packed = true;
+    return NPHM_OK;
+}
+
+void chain_destroy(nphm_mlp *h)
+{
+    delete h->chain;
+    h->chain = nullptr;
+}
+
+// value pass over M = n_queries * n_points rows; keeps h_l and (want_deriv) s_l of every hidden layer; `out` = last layer
+static int value_pass(nphm_mlp *h, const float *xyz, int n_queries, long long n_points, bool want_deriv, float *out,
+                      cudaStream_t stream)
+{
+    MlpChain &c = *h->chain;
+    const StackDims &s = h->dims;
+    const long long M = (long long)n_queries * n_points;
+    int rc;
+    for (int l = 0; l < s.n_lin; ++l) {
+        const bool last = l == s.n_lin - 1;
+        tcl::LinearParams p;
+        p.M = M;
+        if (l == 0) { p.A1 = xyz; p.lda1 = 3; p.K1 = 3; }
+        else {
+            p.A1 = c.H[l - 1].as<float>(); p.lda1 = c.ld[l - 1]; p.K1 = s.N[l - 1];
+            if (l == s.skip) { p.A2 = xyz; p.lda2 = 3; p.K2 = 3; }
+        }
+        p.bias = h->cvec.as<float>() + s.coff[l]; p.ldb = s.cvec_stride; p.rows_per_bias = n_points;
+        if (last) {
+            p.mode = tcl::kModeLinear;
+            p.C = out; p.ldc = s.N[l];
+        } else {
+            if ((rc = c.H[l].reserve((size_t)M * c.ld[l] * sizeof(float)))) return rc;
+            p.mode = tcl::kModeSoftplus;
+            p.C = c.H[l].as<float>(); p.ldc = c.ld[l];
+            if (want_deriv) {
+                if ((rc = c.S[l].reserve((size_t)M * c.ld[l] * sizeof(float)))) return rc;
+                p.Dv = c.S[l].as<float>(); p.lddv = c.ld[l];
+            }
+        }
+        if ((rc = tcl::launch_linear(c.fwd[l], p, stream))) return rc;
+    }
+    return NPHM_OK;
+}
+
+}  // namespace nphm
+
+using namespace nphm;
+
+static int chain_ready(nphm_mlp *h, const char *who)
+{
+    NPHM_REQUIRE(h && h->loaded, "%s: weights not loaded", who);
+    NPHM_REQUIRE(h->chain && h->chain->packed, "%s: layer chain not packed", who);
+    NPHM_REQUIRE(h->dims.skip >= 1 && h->dims.skip < h->dims.n_lin - 1, "%s: unsupported skip position", who);
+    return NPHM_OK;
+}
+
+// forward of an arbitrary-width stack, layer by layer (used when no fused kernel takes the shape)
+extern "C" int nphm_mlp_query_layers(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                                     float *out_dev, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = chain_ready(h, "nphm_mlp_query_layers");
+    if (rc) return rc;
+    NPHM_REQUIRE(n_queries >= 1 && n_points >= 0 && cond_dev, "nphm_mlp_query_layers: bad arguments");
+    if (n_points == 0) return NPHM_OK;
+    NPHM_REQUIRE(xyz_dev && out_dev, "nphm_mlp_query_layers: NULL pointer");
+    if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
+    return value_pass(h, xyz_dev, n_queries, n_points, false, out_dev, stream);
+}
+
+// value + forward-mode tangents: out [q][n][out_dim] (optional), jac [q][n][out_dim][3] = d out / d xyz
+extern "C" int nphm_mlp_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                                 float *out_dev, float *jac_dev, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = chain_ready(h, "nphm_mlp_jacobian");
+    if (rc) return rc;
+    NPHM_REQUIRE(n_queries >= 1 && n_points >= 0 && cond_dev && jac_dev, "nphm_mlp_jacobian: bad arguments");
+    if (n_points == 0) return NPHM_OK;
+    MlpChain &c = *h->chain;
+    const StackDims &s = h->dims;
+    const long long M = (long long)n_queries * n_points;
+    const int out_dim = s.N[s.n_lin - 1];
+    if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
+    float *out = out_dev;
+    if (!out) {
+        if ((rc = c.out_tmp.reserve((size_t)M * out_dim * sizeof(float)))) return rc;
+        out = c.out_tmp.as<float>();
+    }
+    if ((rc = value_pass(h, xyz_dev, n_queries, n_points, true, out, stream))) return rc;
+    // tangent pass: rows (point, j), j = 0..2
+    int maxld = 4;
+    for (int l = 0; l < s.n_lin; ++l) maxld = c.ld[l] > maxld ? c.ld[l] : maxld;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = c.T[i].reserve((size_t)3 * M * maxld * sizeof(float)))) return rc;
+    for (int l = 0; l < s.n_lin; ++l) {
+        const bool last = l == s.n_lin - 1;
+        tcl::LinearParams p;
+        p.M = 3 * M;
+        if (l == 0) { p.K1 = 0; p.K2 = 3; p.a2_onehot = 1; }
+        else {
+            p.A1 = c.T[(l - 1) & 1].as<float>(); p.lda1 = c.ld[l - 1]; p.K1 = s.N[l - 1];
+            if (l == s.skip) { p.K2 = 3; p.a2_onehot = 1; }
+        }
+        p.C = c.T[l & 1].as<float>(); p.ldc = c.ld[l];
+        if (last) p.mode = tcl::kModeLinear;
+        else { p.mode = tcl::kModeMult; p.Mul = c.S[l].as<float>(); p.ldmul = c.ld[l]; p.mul_div = 3; }
+        if ((rc = tcl::launch_linear(c.fwd[l], p, stream))) return rc;
+    }
+    const long long total = M * out_dim * 3;
+    chain::jacobian_layout_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(c.T[(s.n_lin - 1) & 1].as<float>(),
+                                                                                      c.ld[s.n_lin - 1], M, out_dim, jac_dev);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+// adjoint pass: grad_cond [q][cond_dim] = sum_n (d out_n / d cond)^T grad_out_n ; grad_xyz [q][n][3] optional
+extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                                        const float *grad_out_dev, float *grad_cond_dev, float *grad_xyz_dev, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = chain_ready(h, "nphm_mlp_backward_inputs");
+    if (rc) return rc;
+    NPHM_REQUIRE(n_queries >= 1 && n_points > 0 && xyz_dev && cond_dev && grad_out_dev && (grad_cond_dev || grad_xyz_dev),
+                 "nphm_mlp_backward_inputs: bad arguments");
+    MlpChain &c = *h->chain;
+    const StackDims &s = h->dims;
+    const long long M = (long long)n_queries * n_points;
+    const int L = s.n_lin - 1, out_dim = s.N[L];
+    if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
+    if ((rc = c.out_tmp.reserve((size_t)M * out_dim * sizeof(float)))) return rc;
+    if ((rc = value_pass(h, xyz_dev, n_queries, n_points, true, c.out_tmp.as<float>(), stream))) return rc;
+    int maxld = 4;
+    for (int l = 0; l < s.n_lin; ++l) maxld = c.ld[l] > maxld ? c.ld[l] : maxld;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = c.D[i].reserve((size_t)M * maxld * sizeof(float)))) return rc;
+    if ((rc = c.sums0.reserve((size_t)n_queries * s.N[0] * sizeof(float)))) return rc;
+    if ((rc = c.sumss.reserve((size_t)n_queries * s.N[s.skip] * sizeof(float)))) return rc;
+    NPHM_CUDA_CHECK(cudaMemsetAsync(c.sums0.ptr, 0, (size_t)n_queries * s.N[0] * sizeof(float), stream));
+    NPHM_CUDA_CHECK(cudaMemsetAsync(c.sumss.ptr, 0, (size_t)n_queries * s.N[s.skip] * sizeof(float), stream));
+    auto col_sums = [&](const float *X, int ld, int n_cols, float *out) {
+        const int chunks = (int)(n_points >= 4096 ? 32 : (n_points >= 256 ? 8 : 1));
+        dim3 grid((unsigned)ceil_div(n_cols, 128), (unsigned)n_queries, (unsigned)chunks);
+        chain::column_sums_kernel<<<grid, 128, 0, stream>>>(X, ld, n_points, n_cols, out);
+    };
+    // d_{l-1} = s_{l-1} * (d_l W_l), from the output layer down to d_0;  d_l lives in D[l & 1]
+    const float *d_cur = grad_out_dev;
+    int ld_cur = out_dim;
+    for (int l = L; l >= 1; --l) {
+        tcl::LinearParams p;
+        p.M = M;
+        p.A1 = d_cur; p.lda1 = ld_cur; p.K1 = s.N[l];
+        p.mode = tcl::kModeMult; p.Mul = c.S[l - 1].as<float>(); p.ldmul = c.ld[l - 1]; p.mul_div = 1;
+        p.C = c.D[(l - 1) & 1].as<float>(); p.ldc = c.ld[l - 1];
+        if ((rc = tcl::launch_linear(c.adj[l], p, stream))) return rc;
+        if (l == s.skip) {
+            // d_skip (the layer's pre-activation gradient) is d_cur here: its column sums feed the condition gradient
+            col_sums(d_cur, ld_cur, s.N[s.skip], c.sumss.as<float>());
+            NPHM_CUDA_CHECK(cudaGetLastError());
+            if (grad_xyz_dev) {
+                tcl::LinearParams px;
+                px.M = M; px.A1 = d_cur; px.lda1 = ld_cur; px.K1 = s.N[s.skip];
+                px.mode = tcl::kModeLinear; px.C = grad_xyz_dev; px.ldc = 3;
+                if ((rc = tcl::launch_linear(c.adj_xs, px, stream))) return rc;
+            }
+        }
+        d_cur = c.D[(l - 1) & 1].as<float>();
+        ld_cur = c.ld[l - 1];
+    }
+    col_sums(d_cur, ld_cur, s.N[0], c.sums0.as<float>());
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    if (grad_cond_dev) {
+        dim3 grid((unsigned)ceil_div(s.cond_dim, 128), (unsigned)n_queries);
+        chain::cond_grad_kernel<<<grid, 128, 0, stream>>>(h->weights.W[0].as<float>(), s.in_total[0], s.N[0], c.sums0.as<float>(),
+                                                          h->weights.W[s.skip].as<float>(), s.in_total[s.skip], s.N[s.skip],
+                                                          s.N[s.skip - 1] + 3, c.sumss.as<float>(), s.cond_dim, grad_cond_dev);
+        NPHM_CUDA_CHECK(cudaGetLastError());
+    }
+    if (grad_xyz_dev) {
+        // + d_0 W_0[:, 0:3]  (the skip-layer part was written above): through a temporary, then accumulate
+        tcl::LinearParams px;
+        px.M = M; px.A1 = d_cur; px.lda1 = ld_cur; px.K1 = s.N[0];
+        px.mode = tcl::kModeLinear;
+        float *tmp = c.D[1].as<float>() == d_cur ? c.D[0].as<float>() : c.D[1].as<float>();
+        px.C = tmp; px.ldc = 4;
+        if ((rc = tcl::launch_linear(c.adj_x0, px, stream))) return rc;
+        chain::add3_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(tmp, 4, M, grad_xyz_dev);
+        NPHM_CUDA_CHECK(cudaGetLastError());
+    }
+    return NPHM_OK;
+}

@@ -1,0 +1,285 @@
+// Generic fp32-accurate linear layer on tcgen05:  C = epilogue( [A1 | A2] * W^T )
+//
+// One building block for everything on the hot path that is a chain of dense layers but does not fit the two fully fused
+// kernels (tc_ensemble_v8.cu: hidden 200 ensemble, tc_mlp.cu: hidden 512 forward): the forward-mode Jacobian and the
+// backward pass of the forward-deformation network (reference src/NPHM/models/diff_operators.py:26-54 `jac`,
+// src/NPHM/models/fitting.py:99-106,167 - implicit differentiation of the Broyden root and loss.backward()), and DeepSDF
+// stacks of any width (NPM baseline 515 -> 1024 x 8, scripts/configs/npm.yaml:2-4).
+//
+// Arithmetic: kind::f16 MMAs with fp32 accumulation in TMEM, both operands split x = hi + lo in two fp16 terms, products
+// hi*hi + hi*lo + lo*hi (3 MMAs per k-step) - the same fp32-level scheme as the fused kernels.  A is read as fp32 from
+// global memory and split on the fly by the four "row" warps (thread = row of the 128-row tile) into a 4-stage shared-memory
+// ring in UMMA K-major core-matrix order; W comes pre-split and pre-packed (pack_linear_kernel) through bulk async copies;
+// SS-form MMAs by one elected lane; the same four warps run the epilogue (thread = accumulator row).
+//
+//   A1 [M x K1] fp32 row-major, optional A2 [M x K2] appended along K (skip connection `cat([h, x])`, the 1/sqrt(2) is folded
+//   into W), or a one-hot A2 (row r -> e_{r mod K2}: the input tangents of a forward-mode pass, never materialised)
+//   W  [N x (K1 + K2)]  ->  slabs [n_tile][k-step][Nt x 16 hi | Nt x 16 lo]
+//   epilogue modes:  LINEAR   C = t + bias[row / rows_per_bias][n]
+//                    SOFTPLUS C = softplus_100(t + bias), optionally D = sigmoid(100 (t + bias))   (the activation's derivative)
+//                    MULT     C = t * Mul[row / mul_div][n]                                         (tangent / adjoint passes)
+#include "tc_linear.cuh"
+#include <cuda_fp16.h>
+
+namespace nphm {
+namespace tcl {
+using namespace tc;
+
+constexpr int kStages = 4;
+constexpr int kRowWarps = 4;
+constexpr int kThreads = 32 * (kRowWarps + 2);
+constexpr int kMaxNt = 256;
+
+struct __align__(128) Stage {
+    uint8_t a_hi[128 * 32], a_lo[128 * 32];      // 128 rows x 16 fp16, core-matrix order
+    uint8_t b[kMaxNt * 64];                      // Nt x 16 hi | Nt x 16 lo
+};
+struct __align__(128) Smem {
+    Stage st[kStages];
+    uint64_t a_full[kStages], b_full[kStages], empty[kStages], d_ready;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const int nt_idx = blockIdx.y;
+    const int n0 = nt_idx * p.Nt;
+    const uint32_t tmem_cols = p.Nt <= 32 ? 32 : (p.Nt <= 64 ? 64 : (p.Nt <= 128 ? 128 : 256));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm.a_full[i], kRowWarps); mbar_init(&sm.b_full[i], 1); mbar_init(&sm.empty[i], 1); }
+        mbar_init(&sm.d_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kRowWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const int slab_bytes = p.Nt * 64;
+
+    if (warp == kRowWarps) {
+        // ================================================================ producer: weight slabs (bulk async copies)
+        if (lane == 0) {
+            const uint8_t *w = p.W + (size_t)nt_idx * p.ksteps * slab_bytes;
+            for (int j = 0; j < p.ksteps; ++j) {
+                const int s = j % kStages;
+                mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
+                mbar_expect_tx(&sm.b_full[s], slab_bytes);
+                bulk_g2s(sm.st[s].b, w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
+            }
+        }
+    } else if (warp == kRowWarps + 1) {
+        // ================================================================ MMA issuer (whole warp runs the loop, one lane issues)
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_m(128, p.Nt);
+        for (int j = 0; j < p.ksteps; ++j) {
+            const int s = j % kStages;
+            const uint32_t ph = (j / kStages) & 1;
+            mbar_wait(&sm.a_full[s], ph);
+            mbar_wait(&sm.b_full[s], ph);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t a_hi = make_desc(smem_u32(sm.st[s].a_hi), 128, 256), a_lo = make_desc(smem_u32(sm.st[s].a_lo), 128, 256);
+                const uint64_t b_hi = make_desc(smem_u32(sm.st[s].b), 128, 256);
+                const uint64_t b_lo = b_hi + (uint64_t)(p.Nt * 2);          // lo half: Nt * 32 bytes further
+                tc_mma_ss(tmem, a_hi, b_hi, idesc, j == 0 ? 0 : 1);
+                tc_mma_ss(tmem, a_hi, b_lo, idesc, 1);
+                tc_mma_ss(tmem, a_lo, b_hi, idesc, 1);
+                tc_commit(&sm.empty[s]);
+                if (j == p.ksteps - 1) tc_commit(&sm.d_ready);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================================================ row warps: split A into the ring, then the epilogue
+        const int t = threadIdx.x;                        // row of the tile = TMEM lane
+        const long long row = row0 + t;
+        const bool row_ok = row < p.M;
+        const float *a1 = p.A1 ? p.A1 + (size_t)(row_ok ? row : 0) * p.lda1 : nullptr;
+        const float *a2 = (p.A2 && !p.a2_onehot) ? p.A2 + (size_t)(row_ok ? row : 0) * p.lda2 : nullptr;
+        const int hot = p.a2_onehot ? (int)(row % p.K2) : -1;
+        const bool vec_ok = p.A1 && (p.lda1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0);
+        const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16;     // (row/8)*256 + (row%8)*16, + 128 for kk >= 8
+        for (int j = 0; j < p.ksteps; ++j) {
+            const int s = j % kStages;
+            float v[16];
+            const int k0 = 16 * j;
+            if (row_ok && vec_ok && k0 + 16 <= p.K1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(a1 + k0) + i);
+                    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int k = k0 + c;
+                    float x = 0.f;
+                    if (row_ok) {
+                        if (k < p.K1) x = __ldg(a1 + k);
+                        else if (k < p.K1 + p.K2) x = p.a2_onehot ? (k - p.K1 == hot ? 1.f : 0.f) : __ldg(a2 + (k - p.K1));
+                    }
+                    v[c] = x;
+                }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
+            uint8_t *ah = sm.st[s].a_hi + off0, *al = sm.st[s].a_lo + off0;
+            *reinterpret_cast<uint4 *>(ah) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(ah + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4 *>(al) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(al + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a_full[s]);
+        }
+        // ---------------- epilogue: thread = row, 16 accumulator columns at a time
+        mbar_wait(&sm.d_ready, 0);
+        tc_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
+        const float *mul = p.Mul ? p.Mul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul : nullptr;
+        for (int c0 = 0; c0 < p.Nt; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tl + c0, r);
+            tc_wait_ld();
+            if (!row_ok) continue;
+            float o[16], dv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = n0 + c0 + e;
+                float x = __uint_as_float(r[e]);
+                dv[e] = 0.f;
+                if (n < p.N) {
+                    if (p.mode == kModeMult) x *= __ldg(mul + n);
+                    else {
+                        if (bias) x += __ldg(bias + n);
+                        if (p.mode == kModeSoftplus) {
+                            // softplus(beta = 100) and its derivative in log2 units: u = 100 log2(e) x
+                            const float u = x * kS;
+                            float ex, lg;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-fabsf(u)));
+                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + ex));
+                            x = (fmaxf(u, 0.0f) + lg) * (1.0f / kS);
+                            dv[e] = __fdividef(u >= 0.f ? 1.0f : ex, 1.0f + ex);
+                        }
+                    }
+                }
+                o[e] = x;
+            }
+            float *crow = p.C + (size_t)row * p.ldc + n0 + c0;
+            const bool full = n0 + c0 + 16 <= p.N;
+            if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4 *>(crow)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (n0 + c0 + e < p.N) crow[e] = o[e];
+            }
+            if (p.Dv) {
+                float *drow = p.Dv + (size_t)row * p.lddv + n0 + c0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (n0 + c0 + e < p.N) drow[e] = dv[e];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kRowWarps + 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// W [rows x ldw] fp32 (reference layout [out][in]) -> slabs.  B[n][k] = scale * (transpose ? W[k0 + k][n0w + n] : W[n0w + n][k0 + k])
+// for n < N, k < K, zero elsewhere; n tiles of Nt, k-steps of 16; per slab Nt x 16 hi then Nt x 16 lo in core-matrix order.
+__global__ void pack_linear_kernel(const float *__restrict__ W, int ldw, int N, int K, int n_off, int k_off, int transpose,
+                                   float scale, int Nt, int n_tiles, int ksteps, uint8_t *__restrict__ out)
+{
+    const size_t total = (size_t)n_tiles * ksteps * Nt * 16;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(t % 16);
+        const int nn = (int)((t / 16) % Nt);
+        const int j = (int)((t / (16 * (size_t)Nt)) % ksteps);
+        const int tile = (int)(t / (16 * (size_t)Nt * ksteps));
+        const int n = tile * Nt + nn, k = j * 16 + kk;
+        float v = 0.f;
+        if (n < N && k < K) v = scale * (transpose ? W[(size_t)(k_off + k) * ldw + n_off + n] : W[(size_t)(n_off + n) * ldw + k_off + k]);
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t off = (size_t)(nn >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
+        uint8_t *base = out + ((size_t)tile * ksteps + j) * Nt * 64;
+        *reinterpret_cast<__half *>(base + off) = hi;
+        *reinterpret_cast<__half *>(base + (size_t)Nt * 32 + off) = lo;
+    }
+}
+
+int choose_nt(int N)
+{
+    // widest tile <= 256 that keeps the padding small: N <= 256 -> one tile rounded up to 16; otherwise tiles of 256
+    if (N <= kMaxNt) return (N + 15) / 16 * 16;
+    return kMaxNt;
+}
+
+int PackedLinear::pack(const float *W_dev, int ldw, int N_, int K_, int n_off, int k_off, bool transpose, float scale,
+                       cudaStream_t stream)
+{
+    N = N_; K = K_;
+    Nt = choose_nt(N);
+    n_tiles = (N + Nt - 1) / Nt;
+    ksteps = (K + 15) / 16;
+    int rc;
+    if ((rc = slabs.reserve((size_t)n_tiles * ksteps * Nt * 64))) return rc;
+    pack_linear_kernel<<<256, 256, 0, stream>>>(W_dev, ldw, N, K, n_off, k_off, transpose ? 1 : 0, scale, Nt, n_tiles, ksteps,
+                                                slabs.as<uint8_t>());
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
+{
+    NPHM_REQUIRE(w.slabs.ptr && p.C && p.M > 0, "tc_linear: unpacked weights or NULL output");
+    NPHM_REQUIRE(p.K1 + p.K2 == w.K, "tc_linear: input width %d + %d does not match the packed weights (%d)", p.K1, p.K2, w.K);
+    NPHM_REQUIRE(p.mode != kModeMult || (p.Mul && p.mul_div > 0), "tc_linear: multiplier missing");
+    p.W = w.slabs.as<uint8_t>();
+    p.N = w.N; p.Nt = w.Nt; p.ksteps = w.ksteps;
+    if (p.rows_per_bias <= 0) p.rows_per_bias = p.M;
+    if (p.mul_div <= 0) p.mul_div = 1;
+    const int smem = (int)sizeof(Smem);
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)w.n_tiles);
+    linear_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+}  // namespace tcl
+}  // namespace nphm

@@ -1,0 +1,35 @@
+// Generic fp32-accurate tcgen05 linear layer (tc_linear.cu): parameters, packed weights, launch.
+#pragma once
+#include "engine.cuh"
+#include "tc_common.cuh"
+
+namespace nphm {
+namespace tcl {
+
+constexpr int kModeLinear = 0, kModeSoftplus = 1, kModeMult = 2;
+
+struct LinearParams {
+    const float *A1 = nullptr; int lda1 = 0; int K1 = 0;     // [M x K1] fp32 row-major (may be absent: K1 = 0)
+    const float *A2 = nullptr; int lda2 = 0; int K2 = 0;     // optional second input appended along K
+    int a2_onehot = 0;                                       // A2 is not read: row r contributes e_{r mod K2}
+    long long M = 0;
+    const float *bias = nullptr; int ldb = 0; long long rows_per_bias = 0;   // bias row = row / rows_per_bias (0: one row for all)
+    int mode = kModeLinear;
+    float *C = nullptr; int ldc = 0;
+    float *Dv = nullptr; int lddv = 0;                       // SOFTPLUS: derivative of the activation (optional)
+    const float *Mul = nullptr; int ldmul = 0; long long mul_div = 1;        // MULT: C = t * Mul[row / mul_div][n]
+    // filled by launch_linear from the packed weights
+    const uint8_t *W = nullptr; int N = 0, Nt = 0, ksteps = 0;
+};
+
+struct PackedLinear {
+    DeviceBuffer slabs;
+    int N = 0, K = 0, Nt = 0, n_tiles = 0, ksteps = 0;
+    // B[n][k] = scale * (transpose ? W[k_off + k][n_off + n] : W[n_off + n][k_off + k]),  n < N, k < K
+    int pack(const float *W_dev, int ldw, int N, int K, int n_off, int k_off, bool transpose, float scale, cudaStream_t stream);
+};
+
+int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream);
+
+}  // namespace tcl
+}  // namespace nphm

@@ -190,6 +190,25 @@ def test_surface_loss_gradients_wrt_latent_and_points(cuda_device):
     assert torch.isnan(out) and float(xb.grad.abs().max()) == 0.0 and float(zb.grad.abs().max()) == 0.0
 
 
+def test_ensemble_backward_inputs_matches_autograd(cuda_device):
+    """nphm_ensemble_backward_inputs (C ABI) == torch.autograd through the reference-pinned composite for an arbitrary upstream
+    gradient: forward values, d/d latent, d/d xyz."""
+    from conftest import sample_latent
+    dec = make_ensemble(0, device=cuda_device).train()
+    torch.manual_seed(8)
+    n = 1531
+    xyz = (torch.randn(n, 3, device=cuda_device) * 0.15 + torch.tensor([0.0, 0.05, -0.1], device=cuda_device))
+    up = torch.randn(n, device=cuda_device)
+    z0 = sample_latent(4).to(cuda_device)
+    xa = xyz.clone().requires_grad_(True); za = z0.clone().reshape(1, 1, -1).requires_grad_(True)
+    sdf_ref, _ = dec(xa[None], za, None)
+    sdf_ref.reshape(-1).backward(up)
+    sdf, g_lat, g_pts = dec.engine().backward_inputs(xyz, z0, up)
+    assert float((sdf - sdf_ref.detach().reshape(-1)).abs().max()) < 1e-5
+    assert _rel(g_lat.cpu().numpy(), za.grad.reshape(-1).cpu().numpy()) < 2e-4
+    assert _rel(g_pts.cpu().numpy(), xa.grad.cpu().numpy()) < 2e-4
+
+
 def test_fit_step_on_a_configuration_without_tensor_core_path(cuda_device):
     """A non-NPHM ensemble shape (hidden 128, condition 16+8) is not taken by the tcgen05 kernel: the fitting step then runs
     its fp32 FFMA forward/backward kernels.  Their latent gradient must match autograd through the composite module."""

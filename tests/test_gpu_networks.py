@@ -231,3 +231,48 @@ def test_deformation_tensor_core_kernel(cuda_device):
         got = eng.query(torch.from_numpy(x).to(cuda_device), torch.from_numpy(c).to(cuda_device), impl='tc').cpu().numpy()
         for b in range(2):
             assert np.abs(got[b] - O.mlp_forward(mp, x[b], c[b])).max() < TOL, n
+
+
+# ---------------------------------------------------------------------------------------------- layer chain (tc_linear)
+def _chain_case(kind, device):
+    from nphm_b200.models.deepSDF import DeepSDF
+    if kind == 'deform':
+        dfn = make_deformation(device)
+        return dfn.defDeepSDF, 232, 3
+    torch.manual_seed(12)
+    if kind == 'npm':          # scripts/configs/npm.yaml:2-4: lat 512, hidden 1024, 8 layers
+        return DeepSDF(lat_dim=512, hidden_dim=1024, nlayers=8, geometric_init=True).to(device), 512, 1
+    return DeepSDF(lat_dim=40, hidden_dim=96, nlayers=5, geometric_init=False, out_dim=3).to(device), 40, 3
+
+
+@pytest.mark.parametrize('kind', ['deform', 'npm', 'small'])
+def test_layer_chain_forward_jacobian_adjoint_match_autograd(cuda_device, kind):
+    """nphm_mlp_query_layers / nphm_mlp_jacobian / nphm_mlp_backward_inputs (generic tcgen05 linear layer) against the
+    reference-pinned composite module under torch autograd: values <= 1e-5, Jacobian and gradients <= 2e-4 relative."""
+    net, lat_dim, out_dim = _chain_case(kind, cuda_device)
+    torch.manual_seed(3)
+    B, N = 2, 333
+    xyz = (torch.rand(B, N, 3, device=cuda_device) - 0.5) * 0.8
+    cond = torch.randn(B, lat_dim, device=cuda_device) * (0.05 if kind != 'npm' else 0.2)
+    eng = net.engine()
+    xa = xyz.clone().requires_grad_(True)
+    ca = cond.clone().requires_grad_(True)
+    ref = net._forward_composite(xa, ca[:, None, :])
+    got = eng.query_layers(xyz, cond)
+    err = float((got - ref.detach()).abs().max())
+    print('%s chain forward max abs err %.3g (|out| max %.3g)' % (kind, err, float(ref.abs().max())))
+    assert err < TOL
+    out, J = eng.jacobian(xyz, cond)
+    assert float((out - ref.detach()).abs().max()) < TOL
+    rows = [torch.autograd.grad(ref[..., i].sum(), xa, retain_graph=True)[0] for i in range(out_dim)]
+    J_ref = torch.stack(rows, dim=-2)
+    jerr = float((J - J_ref).abs().max() / J_ref.abs().max())
+    print('%s chain Jacobian rel err %.3g' % (kind, jerr))
+    assert jerr < 2e-4
+    up = torch.randn(B, N, out_dim, device=cuda_device)
+    g_c_ref, g_x_ref = torch.autograd.grad((ref * up).sum(), [ca, xa])
+    g_c, g_x = eng.backward_inputs(xyz, cond, up, want_xyz=True)
+    cerr = float((g_c - g_c_ref).abs().max() / g_c_ref.abs().max())
+    xerr = float((g_x - g_x_ref).abs().max() / g_x_ref.abs().max())
+    print('%s chain adjoint rel err: cond %.3g xyz %.3g' % (kind, cerr, xerr))
+    assert cerr < 2e-4 and xerr < 2e-4

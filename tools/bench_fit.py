@@ -38,8 +38,11 @@ def main():
                 'reg_loc': {500: 3, 600: 10}}
     if args.sharded:
         from nphm_b200.distributed import inference_identity_space_sharded
-        if world == 1:
-            dist.init_process_group('nccl', device_id=dev, init_method='tcp://127.0.0.1:29533', rank=0, world_size=1)
+        if world == 1 and not dist.is_initialized():
+            if 'MASTER_ADDR' in os.environ and 'RANK' in os.environ:
+                dist.init_process_group('nccl', device_id=dev)
+            else:
+                dist.init_process_group('nccl', device_id=dev, init_method='tcp://127.0.0.1:29533', rank=0, world_size=1)
 
         def fit(n):
             return inference_identity_space_sharded(dec, obs, dict(lambdas), n_steps=n, schedule_cfg=schedule)
