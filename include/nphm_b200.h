@@ -222,6 +222,14 @@ int nphm_mlp_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, 
  *           grad_xyz_dev [q][n][3]    = (d out_n / d xyz_n)^T grad_out_n            (may be NULL).   grad_out_dev: [q][n][out_dim]. */
 int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
                              const float *grad_out_dev, float *grad_cond_dev, float *grad_xyz_dev, void *stream);
+/* (I + d out / d xyz)^-1 per point for a 3-output stack == `jac(decoder_expr, x, ...).inverse()` of the reference
+ * (iterative_root_finding.py:123, fitting.py:104): out_dev [q][n][3] (may be NULL), jinv_dev [q][n][3][3]. */
+int nphm_mlp_inverse_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                              float *out_dev, float *jinv_dev, void *stream);
+
+/* anchors_dev [n_queries][n_loc][3] = mlp_pos(z_glob) + mean anchors (reference src/NPHM/models/EnsembledDeepSDF.py:228-229)
+ * without evaluating the ensemble - what the fitters read from `decoder(zeros(1,1,3), lat)[1]` (fitting.py:59, :211). */
+int nphm_ensemble_anchors(nphm_ensemble *h, const float *latents_dev, int n_queries, float *anchors_dev, void *stream);
 
 /* Vector-Jacobian product of the ensemble forward w.r.t. its inputs == what torch.autograd computes for
  * `decoder(xyz, lat)[0].backward(grad_sdf)` on FastEnsembleDeepSDFMirrored in training mode (reference
@@ -238,10 +246,18 @@ int nphm_ensemble_backward_inputs(nphm_ensemble *h, const float *points_dev, lon
  * evaluates nphm_fit_surface_grad on every rank's share of the sampled points, combines [n_r * grad_r, n_r * loss_r, n_r]
  * with ONE all-reduce and then calls this on every rank with the identical global result.
  * surface_grad_dev: d(mean |sdf| over the kept points)/d latent (lat_dim, un-weighted: lambda_surface is applied here);
- * surface_stats_dev: [n_kept, sum |sdf| over the kept points]; loss_terms_dev as in nphm_fit_identity_step (may be NULL). */
+ * surface_stats_dev: [n_kept, sum |sdf| over the kept points]; loss_terms_dev as in nphm_fit_identity_step (may be NULL).
+ * grad_anchors_dev (n_loc*3, may be NULL): an additional gradient w.r.t. the anchors, back-propagated through mlp_pos into
+ * z_glob (joint fitter: the deformation network is conditioned on the anchors, deepSDF.py:218-219); also scaled by
+ * lambda_surface.  apply_update = 0: only the total gradient (grad_out_dev, lat_dim, may be NULL) and the loss terms. */
 int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, float *adam_m_dev, float *adam_v_dev,
                             const nphm_fit_params *fp, const float *surface_grad_dev, const float *surface_stats_dev,
-                            float *loss_terms_dev, void *stream);
+                            const float *grad_anchors_dev, int apply_update, float *loss_terms_dev, float *grad_out_dev,
+                            void *stream);
+/* torch.optim.Adam.step() (lr, betas 0.9/0.999, eps 1e-8) on a dense fp32 tensor: the expression codes of the joint fitter
+ * (reference src/NPHM/models/fitting.py:36,169).  step is the 1-based step count. */
+int nphm_adam_step(float *param_dev, const float *grad_dev, float *adam_m_dev, float *adam_v_dev, long long n, float lr,
+                   int step, void *stream);
 
 #ifdef __cplusplus
 }

@@ -28,10 +28,10 @@ EXPORTED_SYMBOLS = (
     'nphm_ensemble_create', 'nphm_ensemble_destroy', 'nphm_ensemble_set_prune_threshold', 'nphm_ensemble_load_weights',
     'nphm_ensemble_query', 'nphm_ensemble_query_grid', 'nphm_ensemble_get_logits_host',
     'nphm_mlp_create', 'nphm_mlp_destroy', 'nphm_mlp_load_weights', 'nphm_mlp_query',
-    'nphm_mlp_query_layers', 'nphm_mlp_jacobian', 'nphm_mlp_backward_inputs',
+    'nphm_mlp_query_layers', 'nphm_mlp_jacobian', 'nphm_mlp_backward_inputs', 'nphm_mlp_inverse_jacobian', 'nphm_adam_step',
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
     'nphm_fit_workspace_bytes', 'nphm_fit_identity_step', 'nphm_fit_surface_grad', 'nphm_fit_apply_gradient',
-    'nphm_ensemble_backward_inputs',
+    'nphm_ensemble_backward_inputs', 'nphm_ensemble_anchors',
     'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search',
 )
 
@@ -136,10 +136,13 @@ def lib() -> ctypes.CDLL:
                                          POINTER(FitParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.nphm_fit_surface_grad.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]
+    L.nphm_ensemble_anchors.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     L.nphm_ensemble_backward_inputs.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p, c_void_p]
     L.nphm_fit_apply_gradient.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(FitParams), c_void_p, c_void_p,
-                                          c_void_p, c_void_p]
+                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.nphm_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p]
+    L.nphm_mlp_inverse_jacobian.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]
     L.nphm_broyden_workspace_bytes.argtypes = [c_longlong]
     L.nphm_broyden_workspace_bytes.restype = c_longlong
     L.nphm_mlp_broyden_search.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
@@ -282,6 +285,16 @@ class EnsembleEngine(_Versioned):
                   'nphm_ensemble_query')
         return sdf, anchors
 
+    def anchors(self, latents: torch.Tensor) -> torch.Tensor:
+        """latents B x lat_dim -> anchors B x n_loc x 3 (the anchor head only, ``nphm_ensemble_anchors``)."""
+        lat = _f32c(latents).reshape(-1, self.lat_dim)
+        dev = lat.device
+        out = torch.empty(lat.shape[0], self.n_loc, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_ensemble_anchors(self._h, lat.data_ptr(), lat.shape[0], out.data_ptr(), _stream_ptr(dev)),
+                  'nphm_ensemble_anchors')
+        return out
+
     def backward_inputs(self, xyz: torch.Tensor, latent: torch.Tensor, grad_sdf: torch.Tensor):
         """Vector-Jacobian product of the training-mode forward (``nphm_ensemble_backward_inputs``): xyz (N,3), latent
         (lat_dim,), grad_sdf (N,) -> (sdf (N,), d/d latent (lat_dim,), d/d xyz (N,3)) - what autograd gives for
@@ -330,9 +343,15 @@ class MlpEngine(_Versioned):
     def __init__(self, module):
         self._h = c_void_p()
         self.n_lin = module.num_layers - 1
-        cfg = MlpConfig(module.lat_dim, hidden_width(module, self.n_lin), self.n_lin - 1, module.out_dim_net)
+        hidden = hidden_width(module, self.n_lin)
+        cfg = MlpConfig(module.lat_dim, hidden, self.n_lin - 1, module.out_dim_net)
         check(lib().nphm_mlp_create(byref(cfg), byref(self._h)), 'nphm_mlp_create')
         self.out_dim = module.out_dim_net
+        # which kernel family AUTO picks (mirrors tc_mlp_supported in csrc/tc_mlp.cu): the fully fused tcgen05 kernel takes the
+        # forward-deformation backbone only; every other shape runs layer by layer on the generic tcgen05 linear layer
+        # (csrc/tc_linear.cu, any width - e.g. the NPM baseline 515 -> 1024 x 8); the fp32 FFMA kernel is kept for impl='simt'
+        self.fused_shape = (hidden == 512 and self.n_lin == 7 and module.lat_dim == 232 and module.out_dim_net == 3)
+        self.simt_ok = hidden <= 880
         self._sig = None
 
     def __del__(self):
@@ -362,14 +381,16 @@ class MlpEngine(_Versioned):
 
     def query(self, xyz: torch.Tensor, cond: torch.Tensor, impl: Optional[int] = None) -> torch.Tensor:
         """xyz B x N x 3, cond B x lat_dim -> B x N x out_dim."""
+        code = _mlp_impl(impl)
+        if (code == IMPL_AUTO and not self.fused_shape) or (code == IMPL_SIMT and not self.simt_ok):
+            return self.query_layers(xyz, cond)
         B, N, _ = xyz.shape
         dev = xyz.device
         xyz = _f32c(xyz)
         cond = _f32c(cond).to(dev)
         out = torch.empty(B, N, self.out_dim, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            check(lib().nphm_mlp_query(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(),
-                                       _mlp_impl(impl), _stream_ptr(dev)),
+            check(lib().nphm_mlp_query(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(), code, _stream_ptr(dev)),
                   'nphm_mlp_query')
         return out
 
@@ -396,6 +417,19 @@ class MlpEngine(_Versioned):
         with torch.cuda.device(dev):
             check(lib().nphm_mlp_jacobian(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(), J.data_ptr(),
                                           _stream_ptr(dev)), 'nphm_mlp_jacobian')
+        return out, J
+
+    def inverse_jacobian(self, xyz: torch.Tensor, cond: torch.Tensor):
+        """(out B x N x 3, (I + d out / d xyz)^-1  B x N x 3 x 3) - the reference's ``jac(...).inverse()`` in one native call."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = _f32c(xyz)
+        cond = _f32c(cond).to(dev)
+        out = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
+        J = torch.empty(B, N, 3, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib().nphm_mlp_inverse_jacobian(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, out.data_ptr(), J.data_ptr(),
+                                                  _stream_ptr(dev)), 'nphm_mlp_inverse_jacobian')
         return out, J
 
     def backward_inputs(self, xyz: torch.Tensor, cond: torch.Tensor, grad_out: torch.Tensor, want_xyz: bool = False):

@@ -194,6 +194,21 @@ int ensemble_prepare(nphm_ensemble *h, const float *latents_dev, int n_queries, 
     return launch_cvec(h->spec, latents_dev, n_queries, h->cvec.as<float>(), stream);
 }
 
+}  // namespace nphm (closed for the C entry below)
+
+// anchors = mlp_pos(z_glob) + mean anchors of n_queries latent codes (reference src/NPHM/models/EnsembledDeepSDF.py:228-229) without
+// evaluating the ensemble: what the fitters obtain by `decoder(zeros(1,1,3), lat)[1]` (fitting.py:59, :211).
+extern "C" int nphm_ensemble_anchors(nphm_ensemble *h, const float *latents_dev, int n_queries, float *out_anchors_dev, void *stream_)
+{
+    using namespace nphm;
+    NPHM_REQUIRE(h && h->loaded && latents_dev && out_anchors_dev && n_queries >= 1, "nphm_ensemble_anchors: bad arguments");
+    const float *pw[3] = {h->pos_w[0].as<float>(), h->pos_w[1].as<float>(), h->pos_w[2].as<float>()};
+    const float *pb[3] = {h->pos_b[0].as<float>(), h->pos_b[1].as<float>(), h->pos_b[2].as<float>()};
+    return launch_anchors(latents_dev, n_queries, h->lat_dim, h->cfg.lat_dim_glob, h->cfg.pos_mlp_dim, h->cfg.n_loc * 3, pw, pb,
+                          h->mean_anchors.as<float>(), out_anchors_dev, static_cast<cudaStream_t>(stream_));
+}
+
+namespace nphm {
 static int pick_impl(nphm_ensemble *h, int impl, bool *use_tc)
 {
     NPHM_REQUIRE(impl == NPHM_IMPL_AUTO || impl == NPHM_IMPL_SIMT || impl == NPHM_IMPL_TC || impl == NPHM_IMPL_TC_PRUNED,

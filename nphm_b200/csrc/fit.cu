@@ -784,11 +784,28 @@ extern "C" int nphm_ensemble_backward_inputs(nphm_ensemble *h, const float *poin
 // ------------------------------------------------------------------------------------------------ sharded fitting
 namespace nphm { namespace fit {
 __global__ void load_external_gradient_kernel(const float *__restrict__ g, const float *__restrict__ stats_in, float lambda,
-                                              int n, float *__restrict__ grad, float *__restrict__ stats)
+                                              int n, float *__restrict__ grad, float *__restrict__ stats,
+                                              const float *__restrict__ ganch_in, int n_anch, float *__restrict__ ganch)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) grad[i] = lambda * g[i];
+    if (ganch_in && i < n_anch) ganch[i] = lambda * ganch_in[i];
     if (i == 0) { stats[0] = stats_in[0]; stats[1] = stats_in[1]; }
+}
+
+// torch.optim.Adam (betas 0.9 / 0.999, eps 1e-8, no weight decay; torch 2.x single-tensor update order) on a dense tensor
+__global__ void adam_dense_kernel(float *__restrict__ param, const float *__restrict__ grad, float *__restrict__ m,
+                                  float *__restrict__ v, long long n, float step_size, float bc2_sqrt)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = grad[i];
+    float mm = m[i], vv = v[i];
+    mm = mm + (g - mm) * 0.1f;
+    vv = vv * 0.999f + 0.001f * g * g;
+    const float denom = sqrtf(vv) / bc2_sqrt + 1e-8f;
+    param[i] = param[i] - step_size * (mm / denom);
+    m[i] = mm; v[i] = vv;
 }
 }}
 
@@ -799,7 +816,8 @@ __global__ void load_external_gradient_kernel(const float *__restrict__ g, const
 // surface_grad_dev: d(mean |sdf| over the kept points)/d latent (lat_dim, un-weighted); surface_stats_dev: [n_kept, sum |sdf|].
 extern "C" int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, float *adam_m_dev, float *adam_v_dev,
                                        const nphm_fit_params *fp, const float *surface_grad_dev, const float *surface_stats_dev,
-                                       float *loss_terms_dev, void *stream_)
+                                       const float *grad_anchors_dev, int apply_update, float *loss_terms_dev,
+                                       float *grad_out_dev, void *stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NPHM_REQUIRE(h && h->loaded, "nphm_fit_apply_gradient: weights not loaded");
@@ -817,12 +835,13 @@ extern "C" int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, floa
     if ((rc = h->fit_apply_scratch.reserve(floats * sizeof(float)))) return rc;
     float *p = h->fit_apply_scratch.as<float>();
     fit::Buffers b{};
-    b.ganch = p; p += d.n_loc * 3;           // zero: the anchor route is already inside surface_grad_dev
+    b.ganch = p; p += d.n_loc * 3;           // zero unless the caller brings an anchor gradient of its own (joint fitter)
     b.stats = p; p += 8;
     b.grad = p;
     NPHM_CUDA_CHECK(cudaMemsetAsync(h->fit_apply_scratch.ptr, 0, floats * sizeof(float), stream));
     fit::load_external_gradient_kernel<<<(d.lat_dim + 255) / 256, 256, 0, stream>>>(surface_grad_dev, surface_stats_dev,
-                                                                                   fp->lambda_surface, d.lat_dim, b.grad, b.stats);
+                                                                                   fp->lambda_surface, d.lat_dim, b.grad, b.stats,
+                                                                                   grad_anchors_dev, d.n_loc * 3, b.ganch);
     NPHM_CUDA_CHECK(cudaGetLastError());
     fit::FinalizeArgs a{};
     a.lambda_surface = fp->lambda_surface; a.lambda_reg_global = fp->lambda_reg_global; a.lambda_reg_loc = fp->lambda_reg_loc;
@@ -833,9 +852,24 @@ extern "C" int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, floa
     a.step_size = (float)((double)fp->lr / bc1);
     a.bc2_sqrt = (float)std::sqrt(bc2);
     a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
-    a.eps = 1e-8f; a.apply_update = 1;
+    a.eps = 1e-8f; a.apply_update = apply_update;
     const size_t fsm = (size_t)(4 * d.pos_hid + 64) * sizeof(float);
-    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, nullptr);
+    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
+    NPHM_CUDA_CHECK(cudaGetLastError());
+    return NPHM_OK;
+}
+
+// torch.optim.Adam.step() on a dense fp32 tensor (reference src/NPHM/models/fitting.py:36,169: the expression codes of the joint
+// fitter - every row is updated every iteration, also the rows that were not sampled).  step = 1-based step count.
+extern "C" int nphm_adam_step(float *param_dev, const float *grad_dev, float *adam_m_dev, float *adam_v_dev, long long n, float lr,
+                              int step, void *stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(param_dev && grad_dev && adam_m_dev && adam_v_dev && n >= 0 && step >= 1, "nphm_adam_step: bad arguments");
+    if (n == 0) return NPHM_OK;
+    const double bc1 = 1.0 - std::pow(0.9, step), bc2 = 1.0 - std::pow(0.999, step);
+    nphm::fit::adam_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(param_dev, grad_dev, adam_m_dev, adam_v_dev, n,
+                                                                                  (float)((double)lr / bc1), (float)std::sqrt(bc2));
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }

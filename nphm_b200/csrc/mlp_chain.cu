@@ -59,6 +59,20 @@ __global__ void jacobian_layout_kernel(const float *__restrict__ T, int ld, long
     J[idx] = T[(size_t)(n * 3 + j) * ld + i];
 }
 
+// in place: J (3 x 3 per point, row i = gradient of output i) -> (I + J)^-1  (adjugate / determinant)
+__global__ void inverse_plus_identity_kernel(float *__restrict__ J, long long n)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float *m = J + p * 9;
+    const float a = m[0] + 1.f, b = m[1], c = m[2], d = m[3], e = m[4] + 1.f, f = m[5], g = m[6], h = m[7], i = m[8] + 1.f;
+    const float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const float inv = 1.0f / (a * A + b * B + c * C);
+    m[0] = A * inv; m[1] = -(b * i - c * h) * inv; m[2] = (b * f - c * e) * inv;
+    m[3] = B * inv; m[4] = (a * i - c * g) * inv;  m[5] = -(a * f - c * d) * inv;
+    m[6] = C * inv; m[7] = -(a * h - b * g) * inv; m[8] = (a * e - b * d) * inv;
+}
+
 __global__ void add3_kernel(const float *__restrict__ src, int ld, long long rows, float *__restrict__ dst)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,5 +305,17 @@ extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const
         chain::add3_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(tmp, 4, M, grad_xyz_dev);
         NPHM_CUDA_CHECK(cudaGetLastError());
     }
+    return NPHM_OK;
+}
+
+extern "C" int nphm_mlp_inverse_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
+                                         float *out_dev, float *jinv_dev, void *stream_)
+{
+    NPHM_REQUIRE(h && h->loaded && h->dims.N[h->dims.n_lin - 1] == 3, "nphm_mlp_inverse_jacobian: needs a 3-output stack");
+    int rc = nphm_mlp_jacobian(h, xyz_dev, cond_dev, n_queries, n_points, out_dev, jinv_dev, stream_);
+    if (rc || n_points == 0) return rc;
+    const long long M = (long long)n_queries * n_points;
+    chain::inverse_plus_identity_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(jinv_dev, M);
+    NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }

@@ -231,7 +231,7 @@ class _NativeShardOps:
         with torch.cuda.device(self.device):
             nat.check(nat.lib().nphm_fit_apply_gradient(self.engine.handle, self.latent.data_ptr(), self.m.data_ptr(),
                                                         self.v.data_ptr(), self._ct.byref(fp), mean_grad.data_ptr(),
-                                                        stats.data_ptr(), self.loss_terms.data_ptr(),
+                                                        stats.data_ptr(), None, 1, self.loss_terms.data_ptr(), None,
                                                         torch.cuda.current_stream(self.device).cuda_stream),
                       'nphm_fit_apply_gradient')
 

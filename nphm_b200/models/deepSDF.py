@@ -74,16 +74,13 @@ class DeepSDF(nn.Module):
         self._engine.refresh(self)
         return self._engine
 
-    # widest stack the fused kernels take: two fp32 activation buffers of 32 points must fit in 227 KB of shared memory
-    _MAX_FUSED_WIDTH = 880
-
     def _fused_ok(self, xyz, lat_rep) -> bool:
         if not xyz.is_cuda or self.num_freq_bands is not None or self.beta != 100:
             return False
         n_lin = self.num_layers - 1
         hidden = _native.hidden_width(self, n_lin)
-        if hidden > self._MAX_FUSED_WIDTH or self.out_dim_net > 8 or not _native.stack_supported(n_lin - 1, hidden, self.lat_dim):
-            return False             # e.g. the NPM baseline (hidden 1024): PyTorch composite path
+        if self.out_dim_net > 8 or not _native.stack_supported(n_lin - 1, hidden, self.lat_dim):
+            return False             # depths the native stack builder rejects: PyTorch composite path
         if torch.is_grad_enabled() and (xyz.requires_grad or lat_rep.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):
             return False

@@ -14,6 +14,7 @@ returned anchors are those of the LAST iteration's pre-update latent (:211).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List
 
 import torch
@@ -216,6 +217,102 @@ def _latent_regularisers(decoder, lat_rep_shape):
     return out
 
 
+def _native_joint(decoder, decoder_expr, device) -> bool:
+    """The autograd-free joint fitter applies to the shipped configuration: fused identity ensemble (training mode) and a
+    'compress' DeformationNetwork in eval mode on the same CUDA device."""
+    from .deepSDF import DeformationNetwork
+    if device.type != 'cuda' or not _fused_identity(decoder) or not isinstance(decoder_expr, DeformationNetwork):
+        return False
+    if decoder_expr.training or decoder_expr.mode != 'compress':
+        return False
+    bb = decoder_expr.defDeepSDF
+    return next(bb.parameters()).is_cuda and bb.num_freq_bands is None and bb.beta == 100 and bb.out_dim_net == 3
+
+
+class JointFitter:
+    """One iteration of ``inference_iterative_root_finding_joint`` (reference fitting.py:38-175) WITHOUT an autograd graph.
+
+    The reference builds xc = p - J^-1 (F_ex(p; theta) + p - stopgrad(.)) so that value(xc) = p and d xc / d theta =
+    -J^-1 dF_ex/d theta (:99-106), then calls loss.backward() (:167).  Written out:
+        g_x   = d surface / d xc                                   nphm_fit_surface_grad (with d surface / d z_id)
+        u     = -J^-T g_x            per point, J = I + dF_ex/dx    nphm_mlp_inverse_jacobian (forward-mode, tensor cores)
+        g_c   = sum_n (dF_ex/d cond)^T u_n   per sampled scan       nphm_mlp_backward_inputs (adjoint pass, tensor cores)
+        cond  = [compressor([z_id | anchors]) (32) | z_ex (200)]    -> z_ex rows, and through the compressor to z_id and the
+                                                                      anchors (mlp_pos backward inside nphm_fit_apply_gradient)
+    followed by the regularisers and the two Adam updates (nphm_fit_apply_gradient, nphm_adam_step)."""
+
+    def __init__(self, decoder, decoder_expr, num_observations: int, device):
+        self.dec, self.dfn, self.device = decoder, decoder_expr, device
+        self.eng = decoder.engine()
+        self.mlp = decoder_expr.defDeepSDF.engine()
+        E = decoder_expr.lat_dim_expr
+        self.z_id = torch.zeros(decoder.lat_dim, device=device)
+        self.m_id, self.v_id = torch.zeros_like(self.z_id), torch.zeros_like(self.z_id)
+        self.z_ex = torch.zeros(num_observations, E, device=device)
+        self.m_ex, self.v_ex = torch.zeros_like(self.z_ex), torch.zeros_like(self.z_ex)
+        self.terms = torch.zeros(8, device=device)
+        self.loss_terms = torch.zeros(8, device=device)
+        self.t = 0
+        self.anchors = None
+
+    def step(self, obs, obs_idx, lambdas, clamp, lr, apply_update: bool = True):
+        """One iteration; with ``apply_update=False`` nothing is modified and ``(d loss / d z_id, d loss / d z_ex)`` - the
+        tensors the reference hands to its two ``Adam.step()`` calls - are returned."""
+        nat, dev = _native, self.device
+        nb, n_point, _ = obs.shape
+        E, D = self.z_ex.shape[1], self.z_id.shape[0]
+        if apply_update:
+            self.t += 1
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.no_grad(), torch.cuda.device(dev):
+            anchors = self.eng.anchors(self.z_id[None])                                  # 1 x K x 3, pre-update code (:59)
+            self.anchors = anchors
+            # condition of the deformation backbone (deepSDF.py:218-219): compressor([z_id | anchors]) (32) | z_ex (E)
+            lin = self.dfn.compressor[0] if isinstance(self.dfn.compressor, torch.nn.Sequential) else self.dfn.compressor
+            Wc, bc = lin.weight, lin.bias
+            first = torch.cat([self.z_id, anchors.reshape(-1)])
+            c32 = (Wc * first[None, :]).sum(1) + bc
+            cond = torch.cat([c32[None, :].expand(nb, -1), self.z_ex[obs_idx]], dim=1).contiguous()
+            # correspondence search (iterative_root_finding.py:91-168): J0^-1 at the observed points, Broyden on the device
+            obs = obs.to(torch.float32).contiguous()
+            _, j0_inv = self.mlp.inverse_jacobian(obs, cond)
+            p, _, valid, _ = self.mlp.broyden_search(obs, cond, obs, j0_inv, max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2)
+            # implicit differentiation of the root (:99-106): J^-1 at the root
+            _, j_inv = self.mlp.inverse_jacobian(p, cond)
+            # surface term (:111-136): value + d/d z_id + d/d xc
+            pts = p.reshape(-1, 3)
+            mask = valid.reshape(-1).to(torch.uint8).contiguous()
+            g_lat = torch.empty(D, device=dev)
+            g_pts = torch.empty_like(pts)
+            nat.check(nat.lib().nphm_fit_surface_grad(self.eng.handle, pts.data_ptr(), pts.shape[0], self.z_id.data_ptr(),
+                                                      mask.data_ptr(), float(clamp), self.terms.data_ptr(), g_lat.data_ptr(),
+                                                      g_pts.data_ptr(), None, stream), 'nphm_fit_surface_grad')
+            u = -(j_inv * g_pts.reshape(nb, n_point, 3, 1)).sum(-2)                       # -J^-T g_x
+            g_cond, _ = self.mlp.backward_inputs(p, cond, u)                             # nb x (32 + E)
+            g_first = (Wc * g_cond[:, :32].sum(0)[:, None]).sum(0)                       # compressor^T -> [z_id | anchors]
+            g_zid = (g_lat + g_first[:D]).contiguous()
+            g_anchors = g_first[D:].contiguous()
+            stats = torch.stack([self.terms[5], self.terms[0] * self.terms[5]]).nan_to_num_(0.0).contiguous()
+            # expression codes: surface route + reg_expr = mean_b ||z_ex[idx_b]||^2 (:137), dense Adam over all rows (:169)
+            lam_s, lam_e = float(lambdas.get('surface', 0.0)), float(lambdas.get('reg_expr', 0.0))
+            g_zex = torch.zeros_like(self.z_ex)
+            g_zex.index_add_(0, obs_idx, lam_s * g_cond[:, 32:] + (2.0 * lam_e / nb) * self.z_ex[obs_idx])
+            fp = nat.FitParams(lam_s, float(lambdas.get('reg_global', 0.0)), float(lambdas.get('reg_loc', 0.0)),
+                               float(lambdas.get('reg_unobserved', 0.0)), float(lambdas.get('symm_dist', 0.0)), float(clamp),
+                               float(lr), max(self.t, 1))
+            g_total = None if apply_update else torch.empty(D, device=dev)
+            nat.check(nat.lib().nphm_fit_apply_gradient(self.eng.handle, self.z_id.data_ptr(), self.m_id.data_ptr(),
+                                                        self.v_id.data_ptr(), ctypes.byref(fp), g_zid.data_ptr(), stats.data_ptr(),
+                                                        g_anchors.data_ptr(), int(apply_update), self.loss_terms.data_ptr(),
+                                                        None if apply_update else g_total.data_ptr(), stream),
+                      'nphm_fit_apply_gradient')
+            if not apply_update:
+                return g_total, g_zex
+            nat.check(nat.lib().nphm_adam_step(self.z_ex.data_ptr(), g_zex.data_ptr(), self.m_ex.data_ptr(), self.v_ex.data_ptr(),
+                                               self.z_ex.numel(), float(lr), self.t, stream), 'nphm_adam_step')
+            return None
+
+
 def inference_iterative_root_finding_joint(decoder,
                                            decoder_expr,
                                            all_obs: List[torch.Tensor],
@@ -226,12 +323,22 @@ def inference_iterative_root_finding_joint(decoder,
                                            lr_scale=1):
     """Joint identity + expression fitting with Broyden correspondences (reference :14-177).
 
-    The correspondence search runs on the device (`nphm_mlp_broyden_search`), the surface term and its gradients w.r.t. the
-    identity code and the canonical points come from one native call (`nphm_fit_surface_grad`); the deformation network's
-    part of the chain (implicit differentiation of the root, Jacobians) stays on autograd.  Returns
+    Shipped configuration (fused ensemble + 'compress' DeformationNetwork on CUDA): no autograd graph at all, see
+    :class:`JointFitter`.  Anything else: the correspondence search runs on the device (`nphm_mlp_broyden_search`), the
+    surface term comes from `nphm_fit_surface_grad`, the deformation network's part of the chain stays on autograd.  Returns
     ``(lat_rep (n_obs,1,E), lat_rep_shape (1,1,D), anchors)``."""
     device = all_obs[0].device
     num_observations = len(all_obs)
+    if _native_joint(decoder, decoder_expr, device) and not os.environ.get('NPHM_JOINT_AUTOGRAD'):
+        fitter = JointFitter(decoder, decoder_expr, num_observations, device)
+        lr = 0.01 * lr_scale
+        for j in range(int(n_steps * step_scale)):
+            lr = _apply_schedule(j, step_scale, schedule_cfg, lambdas, lr)
+            obs, obs_idx = _sample_observations(all_obs)
+            fitter.step(obs, obs_idx.long().to(device), lambdas, _clamp_for_iteration(j, step_scale), lr)
+        lat_rep = fitter.z_ex.reshape(num_observations, 1, -1).clone().requires_grad_(True)
+        lat_rep_shape = fitter.z_id.reshape(1, 1, -1).clone().requires_grad_(True)
+        return lat_rep, lat_rep_shape, fitter.anchors
     lat_expr_dim = decoder_expr.lat_dim_expr if hasattr(decoder_expr, 'lat_dim_expr') else 200
     lat_rep = torch.zeros([num_observations, 1, lat_expr_dim], device=device, requires_grad=True)
     lat_rep_shape = torch.zeros([1, 1, decoder.lat_dim], device=device, requires_grad=True)
