@@ -127,7 +127,9 @@ int nphm_mlp_query(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int
  *                  which a sample stopped, not the best one seen (its x_opt aliases x)
  *   jinv_init_dev  n_queries*n_points*9 row-major initial inverse Jacobians (not modified)
  *   diff_dev       out: smallest residual norm seen per sample; valid_dev out: diff < cvg_thresh (1 byte each)
- *   steps_done     host int, may be NULL.  workspace_dev: nphm_broyden_workspace_bytes(n_queries*n_points) bytes. */
+ *   steps_done     host int.  NULL = sync-free call (CUDA-graph capturable): no early-exit read-back, all max_steps run; frozen
+ *                  samples do not move any more, so the result is identical.
+ *   workspace_dev: nphm_broyden_workspace_bytes(n_queries*n_points) bytes. */
 long long nphm_broyden_workspace_bytes(long long n_total);
 int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n_queries, long long n_points,
                             const float *obs_dev, float *x_dev, const float *jinv_init_dev, int max_steps,
@@ -219,7 +221,9 @@ int nphm_mlp_jacobian(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, 
                       float *out_dev, float *jac_dev, void *stream);
 /* Adjoint pass == what loss.backward() (reference src/NPHM/models/fitting.py:167) propagates through the deformation
  * network:  grad_cond_dev [q][lat_dim] = sum_n (d out_n / d cond_q)^T grad_out_n  (may be NULL),
- *           grad_xyz_dev [q][n][3]    = (d out_n / d xyz_n)^T grad_out_n            (may be NULL).   grad_out_dev: [q][n][out_dim]. */
+ *           grad_xyz_dev [q][n][3]    = (d out_n / d xyz_n)^T grad_out_n            (may be NULL).   grad_out_dev: [q][n][out_dim].
+ * xyz_dev == NULL: reuse the activations of the preceding nphm_mlp_jacobian / nphm_mlp_inverse_jacobian call on this handle
+ * (same points, same condition) instead of recomputing the value pass. */
 int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const float *cond_dev, int n_queries, long long n_points,
                              const float *grad_out_dev, float *grad_cond_dev, float *grad_xyz_dev, void *stream);
 /* (I + d out / d xyz)^-1 per point for a 3-output stack == `jac(decoder_expr, x, ...).inverse()` of the reference

@@ -432,8 +432,10 @@ class MlpEngine(_Versioned):
                                                   _stream_ptr(dev)), 'nphm_mlp_inverse_jacobian')
         return out, J
 
-    def backward_inputs(self, xyz: torch.Tensor, cond: torch.Tensor, grad_out: torch.Tensor, want_xyz: bool = False):
-        """Adjoint pass (nphm_mlp_backward_inputs): grad_out B x N x out_dim -> (d/d cond  B x lat_dim, d/d xyz B x N x 3 | None)."""
+    def backward_inputs(self, xyz: torch.Tensor, cond: torch.Tensor, grad_out: torch.Tensor, want_xyz: bool = False,
+                        reuse_value_pass: bool = False):
+        """Adjoint pass (nphm_mlp_backward_inputs): grad_out B x N x out_dim -> (d/d cond  B x lat_dim, d/d xyz B x N x 3 | None).
+        ``reuse_value_pass``: the preceding ``jacobian`` / ``inverse_jacobian`` call was at the same (xyz, cond)."""
         B, N, _ = xyz.shape
         dev = xyz.device
         xyz = _f32c(xyz)
@@ -442,12 +444,14 @@ class MlpEngine(_Versioned):
         g_cond = torch.empty(B, cond.shape[-1], device=dev, dtype=torch.float32)
         g_xyz = torch.empty(B, N, 3, device=dev, dtype=torch.float32) if want_xyz else None
         with torch.cuda.device(dev):
-            check(lib().nphm_mlp_backward_inputs(self._h, xyz.data_ptr(), cond.data_ptr(), B, N, g.data_ptr(), g_cond.data_ptr(),
-                                                 _ptr(g_xyz), _stream_ptr(dev)), 'nphm_mlp_backward_inputs')
+            check(lib().nphm_mlp_backward_inputs(self._h, None if reuse_value_pass else xyz.data_ptr(), cond.data_ptr(), B, N,
+                                                 g.data_ptr(), g_cond.data_ptr(), _ptr(g_xyz), _stream_ptr(dev)),
+                  'nphm_mlp_backward_inputs')
         return g_cond, g_xyz
 
     def broyden_search(self, obs: torch.Tensor, cond: torch.Tensor, x_init: torch.Tensor, J_inv_init: torch.Tensor,
-                       max_steps: int = 15, cvg_thresh: float = 1e-6, dvg_thresh: float = 0.2, eps: float = 1e-6):
+                       max_steps: int = 15, cvg_thresh: float = 1e-6, dvg_thresh: float = 0.2, eps: float = 1e-6,
+                       early_exit: bool = True):
         """Roots of ``x + F(x; cond) - obs`` by the reference's Broyden iteration, entirely on the device.
         obs, x_init: B x N x 3, cond: B x lat_dim, J_inv_init: B x N x 3 x 3.
         Returns ``(x B x N x 3, diff B x N, valid B x N bool, steps taken)``."""
@@ -464,7 +468,8 @@ class MlpEngine(_Versioned):
             ws = torch.empty(max(int(lib().nphm_broyden_workspace_bytes(B * N)), 256), device=dev, dtype=torch.uint8)
             check(lib().nphm_mlp_broyden_search(self._h, cond.data_ptr(), B, N, obs.data_ptr(), x.data_ptr(),
                                                 jinv.data_ptr(), int(max_steps), float(cvg_thresh), float(dvg_thresh),
-                                                float(eps), diff.data_ptr(), valid.data_ptr(), byref(steps),
+                                                float(eps), diff.data_ptr(), valid.data_ptr(),
+                                                byref(steps) if early_exit else None,       # None: no host sync, all steps run
                                                 ws.data_ptr(), _stream_ptr(dev)), 'nphm_mlp_broyden_search')
         return x, diff, valid.bool(), steps.value
 

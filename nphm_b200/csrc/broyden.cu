@@ -163,7 +163,9 @@ extern "C" int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n
         broyden::advance_kernel<<<blocks, 256, 0, stream>>>(s, n);
         NPHM_CUDA_CHECK(cudaGetLastError());
         if ((rc = mlp_run(h, s.x, n_queries, n_points, s.f, NPHM_IMPL_AUTO, stream))) return rc;
-        const bool check = (step % broyden::kCheckEvery) == broyden::kCheckEvery - 1 && step + 1 < max_steps;
+        // early exit needs a 4-byte read-back + stream sync; a caller that passes steps_done == NULL asks for a sync-free
+        // (CUDA-graph capturable) call: all max_steps run, frozen samples simply stop moving, the result is identical
+        const bool check = steps_done != nullptr && (step % broyden::kCheckEvery) == broyden::kCheckEvery - 1 && step + 1 < max_steps;
         if (check) NPHM_CUDA_CHECK(cudaMemsetAsync(s.n_active, 0, sizeof(int), stream));
         broyden::update_kernel<<<blocks, 256, 0, stream>>>(s, obs_dev, n, cvg_thresh, dvg_thresh, eps);
         NPHM_CUDA_CHECK(cudaGetLastError());

@@ -90,6 +90,8 @@ struct MlpChain {
     tcl::PackedLinear adj_x0, adj_xs;         // W_0[:, 0:3]^T and W_skip[:, Nh:Nh+3]^T / sqrt2  (gradient w.r.t. xyz)
     DeviceBuffer H[kMaxLayers], S[kMaxLayers], T[2], D[2], sums0, sumss, out_tmp;
     int ld[kMaxLayers];
+    long long value_rows = 0;                 // rows of the last value pass that kept the activation derivatives
+    bool have_deriv = false;
 };
 
 static int pad4(int n) { return (n + 3) / 4 * 4; }
@@ -157,6 +159,8 @@ static int value_pass(nphm_mlp *h, const float *xyz, int n_queries, long long n_
         }
         if ((rc = tcl::launch_linear(c.fwd[l], p, stream))) return rc;
     }
+    c.value_rows = M;
+    c.have_deriv = want_deriv;
     return NPHM_OK;
 }
 
@@ -239,15 +243,22 @@ extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int rc = chain_ready(h, "nphm_mlp_backward_inputs");
     if (rc) return rc;
-    NPHM_REQUIRE(n_queries >= 1 && n_points > 0 && xyz_dev && cond_dev && grad_out_dev && (grad_cond_dev || grad_xyz_dev),
+    NPHM_REQUIRE(n_queries >= 1 && n_points > 0 && cond_dev && grad_out_dev && (grad_cond_dev || grad_xyz_dev),
                  "nphm_mlp_backward_inputs: bad arguments");
     MlpChain &c = *h->chain;
     const StackDims &s = h->dims;
     const long long M = (long long)n_queries * n_points;
     const int L = s.n_lin - 1, out_dim = s.N[L];
-    if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
-    if ((rc = c.out_tmp.reserve((size_t)M * out_dim * sizeof(float)))) return rc;
-    if ((rc = value_pass(h, xyz_dev, n_queries, n_points, true, c.out_tmp.as<float>(), stream))) return rc;
+    if (xyz_dev) {
+        if ((rc = mlp_prepare(h, cond_dev, n_queries, stream))) return rc;
+        if ((rc = c.out_tmp.reserve((size_t)M * out_dim * sizeof(float)))) return rc;
+        if ((rc = value_pass(h, xyz_dev, n_queries, n_points, true, c.out_tmp.as<float>(), stream))) return rc;
+        c.value_rows = M;
+    } else {
+        // xyz_dev == NULL: the activation derivatives of the previous nphm_mlp_jacobian / nphm_mlp_inverse_jacobian call on this
+        // handle are reused (the joint fitter differentiates at the same points it just took the Jacobian at)
+        NPHM_REQUIRE(c.value_rows == M && c.have_deriv, "nphm_mlp_backward_inputs: no matching value pass to reuse");
+    }
     int maxld = 4;
     for (int l = 0; l < s.n_lin; ++l) maxld = c.ld[l] > maxld ? c.ld[l] : maxld;
     for (int i = 0; i < 2; ++i)

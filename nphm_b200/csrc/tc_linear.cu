@@ -123,9 +123,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         const int hot = p.a2_onehot ? (int)(row % p.K2) : -1;
         const bool vec_ok = p.A1 && (p.lda1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0);
         const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16;     // (row/8)*256 + (row%8)*16, + 128 for kk >= 8
-        for (int j = 0; j < p.ksteps; ++j) {
-            const int s = j % kStages;
-            float v[16];
+        // the 16 inputs of k-step j: cols [16 j, 16 j + 16) of [A1 | A2], zero beyond the real width / the last row
+        auto load_step = [&](int j, float (&v)[16]) {
             const int k0 = 16 * j;
             if (row_ok && vec_ok && k0 + 16 <= p.K1) {
 #pragma unroll
@@ -145,9 +144,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                     v[c] = x;
                 }
             }
+        };
+        float cur[16], nxt[16];
+        load_step(0, cur);
+        for (int j = 0; j < p.ksteps; ++j) {
+            const int s = j % kStages;
+            if (j + 1 < p.ksteps) load_step(j + 1, nxt);       // in flight while this k-step is split and stored
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            for (int i = 0; i < 8; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
             mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
             uint8_t *ah = sm.st[s].a_hi + off0, *al = sm.st[s].a_lo + off0;
             *reinterpret_cast<uint4 *>(ah) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -157,6 +162,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a_full[s]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
         // ---------------- epilogue: thread = row, 16 accumulator columns at a time
         mbar_wait(&sm.d_ready, 0);

@@ -254,6 +254,9 @@ class JointFitter:
         self.loss_terms = torch.zeros(8, device=device)
         self.t = 0
         self.anchors = None
+        # Broyden early exit (the reference leaves its loop when nobody is active) costs a host sync every third step; without it
+        # an iteration is a pure launch sequence.  Default: on for small batches is not worth a sync on a B200 - off.
+        self.early_exit = bool(int(os.environ.get('NPHM_BROYDEN_EARLY_EXIT', '0')))
 
     def step(self, obs, obs_idx, lambdas, clamp, lr, apply_update: bool = True):
         """One iteration; with ``apply_update=False`` nothing is modified and ``(d loss / d z_id, d loss / d z_ex)`` - the
@@ -276,7 +279,8 @@ class JointFitter:
             # correspondence search (iterative_root_finding.py:91-168): J0^-1 at the observed points, Broyden on the device
             obs = obs.to(torch.float32).contiguous()
             _, j0_inv = self.mlp.inverse_jacobian(obs, cond)
-            p, _, valid, _ = self.mlp.broyden_search(obs, cond, obs, j0_inv, max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2)
+            p, _, valid, _ = self.mlp.broyden_search(obs, cond, obs, j0_inv, max_steps=15, cvg_thresh=1e-6, dvg_thresh=0.2,
+                                                     early_exit=self.early_exit)
             # implicit differentiation of the root (:99-106): J^-1 at the root
             _, j_inv = self.mlp.inverse_jacobian(p, cond)
             # surface term (:111-136): value + d/d z_id + d/d xc
@@ -288,7 +292,7 @@ class JointFitter:
                                                       mask.data_ptr(), float(clamp), self.terms.data_ptr(), g_lat.data_ptr(),
                                                       g_pts.data_ptr(), None, stream), 'nphm_fit_surface_grad')
             u = -(j_inv * g_pts.reshape(nb, n_point, 3, 1)).sum(-2)                       # -J^-T g_x
-            g_cond, _ = self.mlp.backward_inputs(p, cond, u)                             # nb x (32 + E)
+            g_cond, _ = self.mlp.backward_inputs(p, cond, u, reuse_value_pass=True)     # nb x (32 + E); same points as j_inv
             g_first = (Wc * g_cond[:, :32].sum(0)[:, None]).sum(0)                       # compressor^T -> [z_id | anchors]
             g_zid = (g_lat + g_first[:D]).contiguous()
             g_anchors = g_first[D:].contiguous()

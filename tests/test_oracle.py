@@ -1,6 +1,7 @@
 """CPU suite, part 1: pin the ORACLE (oracle/) against the golden vectors produced by the reference itself
 (tests/golden/make_golden.py) and check the marching-cubes restatement through domain properties."""
 import numpy as np
+import pytest
 import torch
 
 from conftest import (load_golden, make_deformation, make_ensemble, make_npm, mesh_edge_stats, noise_volume,
@@ -156,3 +157,15 @@ def test_oracle_broyden_search_against_reference():
         assert np.abs(x[both] - g['xc'][q][both]).max() < 5e-5
         assert (diff[valid] < 1e-6).all()
     assert agree >= 0.97 * g['valid'].size, agree
+
+
+def test_mc_oracle_against_pymcubes_when_available():
+    """Opportunistic pin of the marching-cubes restatement against PyMCubes itself (the reference's un-vendored, un-pinned
+    dependency, utils/reconstruction.py:30).  Goes live on any box where `import mcubes` works; skipped in this image."""
+    mcubes = pytest.importorskip('mcubes')
+    from conftest import noise_volume, sphere_volume
+    for vol in (sphere_volume(24), noise_volume((9, 7, 8), seed=3), noise_volume((5, 6, 7), seed=11)):
+        v_ref, t_ref = mcubes.marching_cubes(vol.astype(np.float64), 0.0)
+        v, t = O.marching_cubes(vol, 0.0)
+        assert np.array_equal(np.asarray(t_ref).astype(np.uint64), t)
+        assert np.array_equal(np.asarray(v_ref, dtype=np.float64), v)

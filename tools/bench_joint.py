@@ -47,8 +47,7 @@ def main():
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             run(3)
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=60))
-        print(prof.key_averages().table(sort_by='count', row_limit=45, max_name_column_width=70))
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=30, max_name_column_width=60))
         ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
         print('cuda kernel launches per iteration: %.0f   cuda time per iteration: %.2f ms'
               % (len(ev) / 3.0, sum(e.device_time for e in ev) / 3e3))
