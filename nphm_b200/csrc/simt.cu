@@ -178,20 +178,25 @@ __global__ void cvec_kernel(const PackSpec spec, const float *__restrict__ laten
     __syncthreads();
     const int set = m < 2 * spec.n_symm ? (m >> 1) : m - spec.n_symm;
     float *out = cvec + ((size_t)qi * spec.n_members + m) * spec.cvec_stride;
+    // one warp per output row (coalesced reads of the weight row, shuffle reduction); blockIdx.z strides over the rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int l = 0; l < spec.n_layers; ++l) {
         const PackLayer &pl = spec.L[l];
-        for (int n = threadIdx.x; n < pl.Npad; n += blockDim.x) {
+        for (int n = blockIdx.z * wpb + warp; n < pl.Npad; n += gridDim.z * wpb) {
             float v = 0.f;
             if (n < pl.N) {
-                v = pl.b[(size_t)set * pl.N + n];
                 if (pl.folded) {
                     const float *w = pl.W + ((size_t)set * pl.N + n) * pl.in_total + pl.K;
                     float s = 0.f;
-                    for (int j = 0; j < C; ++j) s = fmaf(w[j], u[j], s);
-                    v = fmaf(s, pl.scale, v);
+                    for (int j = lane; j < C; j += 32) s = fmaf(w[j], u[j], s);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    v = fmaf(s, pl.scale, pl.b[(size_t)set * pl.N + n]);
+                } else {
+                    v = pl.b[(size_t)set * pl.N + n];
                 }
             }
-            out[pl.coff + n] = v;
+            if (lane == 0) out[pl.coff + n] = v;
         }
     }
 }
@@ -258,7 +263,9 @@ __global__ void pack_wt_kernel(const float *__restrict__ W, int n_sets, int N, i
 
 int launch_cvec(const PackSpec &spec, const float *latents, int n_queries, float *cvec, cudaStream_t stream)
 {
-    dim3 grid(spec.n_members, n_queries);
+    // few (member, query) pairs (a plain MLP has one member): spread the rows of a pair over several CTAs
+    const int pairs = spec.n_members * n_queries;
+    dim3 grid(spec.n_members, n_queries, pairs >= 128 ? 1 : (pairs >= 16 ? 4 : 16));
     cvec_kernel<<<grid, 256, spec.cond_dim * sizeof(float), stream>>>(spec, latents, cvec);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;

@@ -34,8 +34,11 @@ struct __align__(128) Stage {
     uint8_t a_hi[128 * 32], a_lo[128 * 32];      // 128 rows x 16 fp16, core-matrix order
     uint8_t b[kMaxNt * 64];                      // Nt x 16 hi | Nt x 16 lo
 };
+constexpr int kAPitch = 20;                      // floats per staged fp32 row (16 + 4: 80-byte pitch spreads the banks)
+constexpr int kADepth = 3;                       // k-steps of A kept in flight per thread (cp.async groups)
 struct __align__(128) Smem {
     Stage st[kStages];
+    float a32[kStages][128][kAPitch];            // fp32 staging of A: every thread copies (cp.async) and reads ITS OWN row
     uint64_t a_full[kStages], b_full[kStages], empty[kStages], d_ready;
     uint32_t tmem_base;
 };
@@ -145,11 +148,35 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 }
             }
         };
-        float cur[16], nxt[16];
-        load_step(0, cur);
+        // k-steps that lie inside A1 and are 16-byte aligned are staged through shared memory with cp.async, kADepth k-steps ahead
+        // (a thread only ever reads the row it copied itself, so cp.async.wait_group is all the synchronisation needed); the few
+        // others (skip-connection tail, one-hot tangents, K padding) are loaded directly
+        auto fast = [&](int j) { return row_ok && vec_ok && 16 * j + 16 <= p.K1; };
+        auto prefetch = [&](int j) {
+            if (j < p.ksteps && fast(j)) {
+                const uint32_t dst = smem_u32(&sm.a32[j % kStages][t][0]);
+                const float *src = a1 + 16 * j;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 4 * i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int d = 0; d < kADepth; ++d) prefetch(d);
         for (int j = 0; j < p.ksteps; ++j) {
             const int s = j % kStages;
-            if (j + 1 < p.ksteps) load_step(j + 1, nxt);       // in flight while this k-step is split and stored
+            float cur[16];
+            asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
+            if (fast(j)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = *reinterpret_cast<const float4 *>(&sm.a32[s][t][4 * i]);
+                    cur[4 * i] = f.x; cur[4 * i + 1] = f.y; cur[4 * i + 2] = f.z; cur[4 * i + 3] = f.w;
+                }
+            } else {
+                load_step(j, cur);
+            }
+            prefetch(j + kADepth);                             // slot (j + 3) % 4 was read by this thread at iteration j - 1
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
@@ -162,9 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a_full[s]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         // ---------------- epilogue: thread = row, 16 accumulator columns at a time
         mbar_wait(&sm.d_ready, 0);
         tc_fence_after();
@@ -176,16 +202,31 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             tc_ld16(tl + c0, r);
             tc_wait_ld();
             if (!row_ok) continue;
-            float o[16], dv[16];
+            float o[16], dv[16], aux[16];                      // aux: bias (LINEAR / SOFTPLUS) or multiplier (MULT) of the 16 columns
+            const bool full = n0 + c0 + 16 <= p.N;
+            {
+                const float *src = p.mode == kModeMult ? mul : bias;
+                const int lds = p.mode == kModeMult ? p.ldmul : p.ldb;
+                if (src && full && (lds % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(src + n0 + c0) + i);
+                        aux[4 * i] = f.x; aux[4 * i + 1] = f.y; aux[4 * i + 2] = f.z; aux[4 * i + 3] = f.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? __ldg(src + n0 + c0 + e) : 0.f;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n = n0 + c0 + e;
                 float x = __uint_as_float(r[e]);
                 dv[e] = 0.f;
                 if (n < p.N) {
-                    if (p.mode == kModeMult) x *= __ldg(mul + n);
+                    if (p.mode == kModeMult) x *= aux[e];
                     else {
-                        if (bias) x += __ldg(bias + n);
+                        x += aux[e];
                         if (p.mode == kModeSoftplus) {
                             // softplus(beta = 100) and its derivative in log2 units: u = 100 log2(e) x
                             const float u = x * kS;
@@ -200,7 +241,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 o[e] = x;
             }
             float *crow = p.C + (size_t)row * p.ldc + n0 + c0;
-            const bool full = n0 + c0 + 16 <= p.N;
             if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -212,9 +252,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             }
             if (p.Dv) {
                 float *drow = p.Dv + (size_t)row * p.lddv + n0 + c0;
+                if (full && (p.lddv % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Dv) & 15) == 0)) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (n0 + c0 + e < p.N) drow[e] = dv[e];
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float4 *>(drow)[i] = make_float4(dv[4 * i], dv[4 * i + 1], dv[4 * i + 2], dv[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (n0 + c0 + e < p.N) drow[e] = dv[e];
+                }
             }
         }
     }
