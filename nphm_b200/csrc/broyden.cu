@@ -27,7 +27,7 @@ struct State {
     float *best;     // n     smallest residual norm seen
     unsigned char *active;   // n
     float *f;        // n*3   network output at x
-    int *n_active;   // 1
+    int *n_active;   // counter of the current step: samples still active after its update
 };
 
 __device__ __forceinline__ float norm3(float a, float b, float c) { return sqrtf(a * a + b * b + c * c); }
@@ -123,7 +123,7 @@ extern "C" long long nphm_broyden_workspace_bytes(long long n_total)
 {
     if (n_total < 0) return NPHM_ERR_INVALID;
     const size_t n = (size_t)n_total;
-    return (long long)(align256(n * 9 * 4) + 3 * align256(n * 3 * 4) + align256(n * 4) + align256(n) + 256);
+    return (long long)(align256(n * 9 * 4) + 3 * align256(n * 3 * 4) + align256(n * 4) + align256(n) + 1024);
 }
 
 extern "C" int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n_queries, long long n_points,
@@ -149,7 +149,10 @@ extern "C" int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n
     s.f = reinterpret_cast<float *>(p); p += align256((size_t)n * 12);
     s.best = reinterpret_cast<float *>(p); p += align256((size_t)n * 4);
     s.active = reinterpret_cast<unsigned char *>(p); p += align256((size_t)n);
-    s.n_active = reinterpret_cast<int *>(p);
+    int *counters = reinterpret_cast<int *>(p);              // one counter per step (max 255), zeroed once
+    NPHM_REQUIRE(max_steps < 255, "nphm_mlp_broyden_search: max_steps must be < 255");
+    NPHM_CUDA_CHECK(cudaMemsetAsync(counters, 0, 1024, stream));
+    s.n_active = counters;
     NPHM_CUDA_CHECK(cudaMemcpyAsync(s.jinv, jinv_init_dev, (size_t)n * 36, cudaMemcpyDeviceToDevice, stream));
 
     int rc;
@@ -162,15 +165,20 @@ extern "C" int nphm_mlp_broyden_search(nphm_mlp *h, const float *cond_dev, int n
     for (int step = 0; step < max_steps; ++step) {
         broyden::advance_kernel<<<blocks, 256, 0, stream>>>(s, n);
         NPHM_CUDA_CHECK(cudaGetLastError());
-        if ((rc = mlp_run(h, s.x, n_queries, n_points, s.f, NPHM_IMPL_AUTO, stream))) return rc;
-        // early exit needs a 4-byte read-back + stream sync; a caller that passes steps_done == NULL asks for a sync-free
-        // (CUDA-graph capturable) call: all max_steps run, frozen samples simply stop moving, the result is identical
-        const bool check = steps_done != nullptr && (step % broyden::kCheckEvery) == broyden::kCheckEvery - 1 && step + 1 < max_steps;
-        if (check) NPHM_CUDA_CHECK(cudaMemsetAsync(s.n_active, 0, sizeof(int), stream));
+        // once nobody is active (counter of the previous step == 0) the network evaluation returns at once: a device-side
+        // early exit that needs no host synchronisation (the reference leaves its loop at that point)
+        h->tc_live = step > 0 ? counters + (step - 1) : nullptr;
+        rc = mlp_run(h, s.x, n_queries, n_points, s.f, NPHM_IMPL_AUTO, stream);
+        h->tc_live = nullptr;
+        if (rc) return rc;
+        s.n_active = counters + step;
         broyden::update_kernel<<<blocks, 256, 0, stream>>>(s, obs_dev, n, cvg_thresh, dvg_thresh, eps);
         NPHM_CUDA_CHECK(cudaGetLastError());
         done = step + 1;
-        if (check) {                           // the reference leaves its loop as soon as nobody is active
+        // optional host-side early exit (4-byte read-back + stream sync every kCheckEvery steps); a caller that passes
+        // steps_done == NULL asks for a sync-free, CUDA-graph capturable call
+        const bool check = steps_done != nullptr && (step % broyden::kCheckEvery) == broyden::kCheckEvery - 1 && step + 1 < max_steps;
+        if (check) {
             int alive = 0;
             NPHM_CUDA_CHECK(cudaMemcpyAsync(&alive, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, stream));
             NPHM_CUDA_CHECK(cudaStreamSynchronize(stream));

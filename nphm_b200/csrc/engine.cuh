@@ -68,6 +68,7 @@ struct nphm_mlp {
     // tensor-core path (tc_mlp.cu)
     nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
     bool tc_ready = false;
+    const int *tc_live = nullptr;   // set around a launch by the Broyden loop: device counter, 0 = skip the evaluation
     // layer-by-layer tensor-core passes: any width, Jacobian, adjoint (mlp_chain.cu)
     nphm::MlpChain *chain = nullptr;
 };

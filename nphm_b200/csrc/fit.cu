@@ -515,19 +515,26 @@ __global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const W
     float *h0 = sh, *h1 = h0 + d.pos_hid, *g1 = h1 + d.pos_hid, *g0 = g1 + d.pos_hid, *red = g0 + d.pos_hid;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Hd = d.pos_hid, G = d.G, O = d.n_loc * 3;
-    // forward of mlp_pos (ReLU masks)
-    for (int n = tid; n < Hd; n += nt) {
-        float s = w.pos_b[0][n];
-        for (int j = 0; j < G; ++j) s = fmaf(w.pos_w[0][(size_t)n * G + j], latent[j], s);
-        h0[n] = fmaxf(s, 0.f);
+    // forward of mlp_pos (ReLU masks): one warp per output row (coalesced weight rows + shuffle reduction)
+    {
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        for (int n = warp; n < Hd; n += nw) {
+            float s = 0.f;
+            for (int j = lane; j < G; j += 32) s = fmaf(w.pos_w[0][(size_t)n * G + j], latent[j], s);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) h0[n] = fmaxf(s + w.pos_b[0][n], 0.f);
+        }
+        __syncthreads();
+        for (int n = warp; n < Hd; n += nw) {
+            float s = 0.f;
+            for (int j = lane; j < Hd; j += 32) s = fmaf(w.pos_w[1][(size_t)n * Hd + j], h0[j], s);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) h1[n] = fmaxf(s + w.pos_b[1][n], 0.f);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int n = tid; n < Hd; n += nt) {
-        float s = w.pos_b[1][n];
-        for (int j = 0; j < Hd; ++j) s = fmaf(w.pos_w[1][(size_t)n * Hd + j], h0[j], s);
-        h1[n] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
     // backward
     for (int j = tid; j < Hd; j += nt) {
         float s = 0.f;

@@ -213,22 +213,28 @@ __global__ void anchors_kernel(const float *__restrict__ latents, int lat_dim, i
     const int qi = blockIdx.x;
     for (int j = threadIdx.x; j < lat_glob; j += blockDim.x) zin[j] = latents[(size_t)qi * lat_dim + j];
     __syncthreads();
-    for (int n = threadIdx.x; n < hid; n += blockDim.x) {
-        float s = b0[n];
-        for (int j = 0; j < lat_glob; ++j) s = fmaf(w0[(size_t)n * lat_glob + j], zin[j], s);
-        h0[n] = fmaxf(s, 0.f);
+    // one warp per output row: coalesced reads of the weight row + shuffle reduction
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    auto dot = [&](const float *__restrict__ w, const float *x, int n) {
+        float s = 0.f;
+        for (int j = lane; j < n; j += 32) s = fmaf(w[j], x[j], s);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        return s;
+    };
+    for (int n = warp; n < hid; n += nw) {
+        const float s = dot(w0 + (size_t)n * lat_glob, zin, lat_glob) + b0[n];
+        if (lane == 0) h0[n] = fmaxf(s, 0.f);
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < hid; n += blockDim.x) {
-        float s = b1[n];
-        for (int j = 0; j < hid; ++j) s = fmaf(w1[(size_t)n * hid + j], h0[j], s);
-        h1[n] = fmaxf(s, 0.f);
+    for (int n = warp; n < hid; n += nw) {
+        const float s = dot(w1 + (size_t)n * hid, h0, hid) + b1[n];
+        if (lane == 0) h1[n] = fmaxf(s, 0.f);
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < n_out; n += blockDim.x) {
-        float s = b2[n];
-        for (int j = 0; j < hid; ++j) s = fmaf(w2[(size_t)n * hid + j], h1[j], s);
-        anchors[(size_t)qi * n_out + n] = s + mean[n];
+    for (int n = warp; n < n_out; n += nw) {
+        const float s = dot(w2 + (size_t)n * hid, h1, hid) + b2[n];
+        if (lane == 0) anchors[(size_t)qi * n_out + n] = s + mean[n];
     }
 }
 
@@ -276,7 +282,7 @@ int launch_anchors(const float *latents, int n_queries, int lat_dim, int lat_glo
                    cudaStream_t stream)
 {
     const size_t smem = (lat_glob + 2 * hid) * sizeof(float);
-    anchors_kernel<<<n_queries, 256, smem, stream>>>(latents, lat_dim, lat_glob, hid, n_out,
+    anchors_kernel<<<n_queries, 1024, smem, stream>>>(latents, lat_dim, lat_glob, hid, n_out,
                                                      w[0], b[0], w[1], b[1], w[2], b[2], mean, anchors);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;

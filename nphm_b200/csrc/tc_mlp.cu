@@ -62,6 +62,7 @@ struct Params {
     long long n_points;
     int n_queries;
     float *out;                 // [n_queries][n_points][3]
+    const int *live;            // optional device counter: the launch does nothing when *live == 0 (Broyden: nobody is active)
 };
 
 // TMEM column of output n of tensor layer t
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const Params p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tiles_per_query = (p.n_points + 63) / 64;
     const long long n_tiles = tiles_per_query * p.n_queries;
+    if (p.live && *p.live == 0) return;                    // uniform over the grid: every sample of the search is frozen
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSlots; ++i) { mbar_init(&sm.slab_full[i], 1); mbar_init(&sm.slab_empty[i], 1); }
@@ -395,7 +397,7 @@ int tc_mlp_launch(nphm_mlp *h, const float *xyz, const float *cvec, int n_querie
     tcm::mlp_records_kernel<<<n_queries, 256, 0, stream>>>(cvec, h->dims.cvec_stride, h->tc_coff.as<int>(), h->weights.W[0].as<float>(),
                                                           h->weights.W[6].as<float>(), h->tc_consts.as<float>());
     NPHM_CUDA_CHECK(cudaGetLastError());
-    tcm::Params p{h->tc_weights.as<uint8_t>(), h->tc_consts.as<float>(), xyz, n_points, n_queries, out};
+    tcm::Params p{h->tc_weights.as<uint8_t>(), h->tc_consts.as<float>(), xyz, n_points, n_queries, out, h->tc_live};
     const long long n_tiles = ceil_div(n_points, 64) * n_queries;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     const int smem = (int)sizeof(tcm::Smem);

@@ -74,7 +74,11 @@ def get_logits_backward(decoder_shape, decoder_expr, encoding_shape, encoding_ex
 def deform_mesh(mesh, deformer, lat_rep, anchors, lat_rep_shape=None):
     """Forward-deform the vertices of a canonical mesh with ``deformer`` (one fused launch instead of the
     reference's 5000-vertex chunks + ``empty_cache``)."""
-    rest = torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32, device=lat_rep.device)[None]
+    cached = getattr(mesh, '_nphm_device_vertices', None)
+    if (cached is not None and cached.device == lat_rep.device and cached.shape[0] == len(mesh.vertices)):
+        rest = cached[None]                      # vertices never left the device since marching cubes (mesh_from_logits)
+    else:
+        rest = torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32, device=lat_rep.device)[None]
     code = lat_rep if lat_rep_shape is None else torch.cat([lat_rep_shape, lat_rep], dim=-1)
     with torch.no_grad():
         if anchors is None:

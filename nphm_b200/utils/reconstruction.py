@@ -59,8 +59,23 @@ def mesh_from_logits(logits, mini, maxi, resolution):
     level set of ``-sdf``, and maps index units to world units with ``step = (maxi-mini)/(resolution-1)``."""
     logits = np.reshape(logits, (resolution,) * 3)
     logits *= -1
-    vertices, triangles = marching_cubes(logits, 0.0)
     step = (np.array(maxi) - np.array(mini)) / (resolution - 1)
+    dev_verts = None
+    if torch.cuda.is_available() and not (isinstance(logits, torch.Tensor) and logits.is_cuda):
+        # keep the device copy of the vertices: deform_mesh() takes it from the mesh instead of uploading them again
+        dev = torch.device('cuda', torch.cuda.current_device())
+        vol = np.ascontiguousarray(logits, dtype=np.float32)
+        v_dev, t_dev = _native.marching_cubes_device(torch.from_numpy(vol).to(dev), 0.0)
+        vertices, triangles = _to_host(v_dev), _to_host(t_dev).view(np.uint64)
+        dev_verts = v_dev * torch.as_tensor(step, device=dev) + torch.as_tensor(np.asarray(mini, dtype=np.float64), device=dev)
+    else:
+        vertices, triangles = marching_cubes(logits, 0.0)
     vertices = vertices * np.expand_dims(step, axis=0)
     vertices += [mini[0], mini[1], mini[2]]
-    return make_mesh(vertices, triangles)
+    mesh = make_mesh(vertices, triangles)
+    if dev_verts is not None and len(mesh.vertices) == dev_verts.shape[0]:     # trimesh's process=True may have merged vertices
+        try:
+            mesh._nphm_device_vertices = dev_verts.to(torch.float32)
+        except AttributeError:
+            pass
+    return mesh
