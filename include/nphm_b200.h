@@ -263,6 +263,14 @@ int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, float *adam_m_d
 int nphm_adam_step(float *param_dev, const float *grad_dev, float *adam_m_dev, float *adam_v_dev, long long n, float lr,
                    int step, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics: nearest-neighbour distances between two point clouds ==
+ * scipy.spatial.cKDTree(tgt).query(src) as used by `distance_p2p` (reference src/NPHM/evaluation/metrics.py:171-194) on
+ * 250 k-point clouds (scripts/evaluation/eval.py:111).  dist_dev: n_src fp64, idx_dev: n_src int64.
+ * ---------------------------------------------------------------------------------------------- */
+int nphm_nearest_neighbors(const float *src_dev, long long n_src, const float *tgt_dev, long long n_tgt,
+                           double *dist_dev, long long *idx_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = (
     'nphm_mc_workspace_bytes', 'nphm_mc_count', 'nphm_mc_emit', 'nphm_marching_cubes_host',
     'nphm_fit_workspace_bytes', 'nphm_fit_identity_step', 'nphm_fit_surface_grad', 'nphm_fit_apply_gradient',
     'nphm_ensemble_backward_inputs', 'nphm_ensemble_anchors',
-    'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search',
+    'nphm_broyden_workspace_bytes', 'nphm_mlp_broyden_search', 'nphm_nearest_neighbors',
 )
 
 
@@ -148,6 +148,7 @@ def lib() -> ctypes.CDLL:
     L.nphm_mlp_broyden_search.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
                                           c_float, c_float, c_float, c_void_p, c_void_p, POINTER(c_int), c_void_p,
                                           c_void_p]
+    L.nphm_nearest_neighbors.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
     for name in EXPORTED_SYMBOLS:                      # fail at load time, not at first use, if a symbol is missing
         getattr(L, name)
     _lib = L
@@ -544,3 +545,17 @@ def marching_cubes_host(volume: np.ndarray, iso: float = 0.0, negate: bool = Fal
         check(L.nphm_marching_cubes_host(vol.ctypes.data, nx, ny, nz, float(iso), int(negate), verts.ctypes.data,
                                          tris.ctypes.data, byref(nv), byref(nt)), 'nphm_marching_cubes_host')
     return verts, tris.view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------ evaluation metrics
+def nearest_neighbors(src: torch.Tensor, tgt: torch.Tensor):
+    """(dist (n_src,) float64, idx (n_src,) int64) of the nearest ``tgt`` point of every ``src`` point (CUDA float32 clouds)."""
+    assert src.is_cuda and tgt.is_cuda and src.shape[-1] == 3 and tgt.shape[-1] == 3
+    dev = src.device
+    s, t = _f32c(src).reshape(-1, 3), _f32c(tgt).reshape(-1, 3)
+    dist = torch.empty(s.shape[0], device=dev, dtype=torch.float64)
+    idx = torch.empty(s.shape[0], device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        check(lib().nphm_nearest_neighbors(s.data_ptr(), s.shape[0], t.data_ptr(), t.shape[0], dist.data_ptr(), idx.data_ptr(),
+                                           _stream_ptr(dev)), 'nphm_nearest_neighbors')
+    return dist, idx
