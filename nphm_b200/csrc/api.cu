@@ -143,7 +143,11 @@ extern "C" int nphm_ensemble_create(const nphm_ensemble_config *cfg, nphm_ensemb
     return NPHM_OK;
 }
 
-extern "C" void nphm_ensemble_destroy(nphm_ensemble *h) { delete h; }
+extern "C" void nphm_ensemble_destroy(nphm_ensemble *h)
+{
+    if (h) nphm::fit_packs_destroy(h);
+    delete h;
+}
 
 extern "C" int nphm_ensemble_set_prune_threshold(nphm_ensemble *h, float tau)
 {
@@ -175,6 +179,7 @@ extern "C" int nphm_ensemble_load_weights(nphm_ensemble *h, const float *const *
                      h->cfg.lat_dim_loc, h->net, h->spec);
     rc = tc_ensemble_pack(h, stream);
     if (rc) return rc;
+    fit_packs_destroy(h);                      // packed from the previous weights, rebuilt by the next fitting call
     h->loaded = true;
     return NPHM_OK;
 }

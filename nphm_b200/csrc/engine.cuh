@@ -35,6 +35,8 @@ void fill_descriptors(const StackDims &s, const NetWeights &w, int n_members, in
 
 }  // namespace nphm
 
+namespace nphm { namespace fit { struct BackwardPacks; } }
+
 struct nphm_ensemble {
     nphm_ensemble_config cfg;
     int n_members = 0, n_sets = 0, lat_dim = 0;
@@ -53,6 +55,7 @@ struct nphm_ensemble {
     float tc_prune_tau = 1e-8f;
     // fitting (fit.cu)
     nphm::DeviceBuffer fit_scratch, fit_apply_scratch;
+    nphm::fit::BackwardPacks *fit_packs = nullptr;      // adjoint weights of the backward GEMMs, built on first use
 };
 
 namespace nphm { struct MlpChain; }
@@ -84,6 +87,8 @@ bool tc_mlp_supported(const nphm_mlp *h);
 int tc_mlp_pack(nphm_mlp *h, cudaStream_t stream);
 int tc_mlp_launch(nphm_mlp *h, const float *xyz, const float *cvec, int n_queries, long long n_points, float *out,
                   cudaStream_t stream);
+// fitting (fit.cu)
+void fit_packs_destroy(nphm_ensemble *h);
 // layer chain (mlp_chain.cu)
 int chain_pack(nphm_mlp *h, cudaStream_t stream);
 void chain_destroy(nphm_mlp *h);

@@ -15,16 +15,21 @@
 //   fit_member_kernel<bwd>  (configurations without the tensor-core path) forward again with all activations resident in
 //                           shared memory (199 KB), backward in place, per-member delta sums and blend-path anchor
 //                           gradients -> atomics
-//   tensor-core path        forward = tc::ensemble_tc_kernel<.., ACTS> (member outputs + hidden activations to global
-//                           memory), backward = fit_backward_mma_kernel (mma.sync 3xTF32)
+//   tensor-core path        forward = tc::ensemble_tc_kernel_v8<.., ACTS> (member outputs + activation derivatives to global
+//                           memory), backward = three batched tcgen05 GEMMs (tc_linear.cu) between fit_upstream_kernel and
+//                           fit_reduce_kernel
 //   fit_member_grad_kernel  per member: delta sums -> g_u, g_c -> latent / anchor gradients
 //   fit_finalize_kernel     mlp_pos forward/backward, regularisers, loss terms, Adam
 #include "engine.cuh"
 #include "simt_layers.cuh"
+#include "tc_ensemble.cuh"
+#include "tc_linear.cuh"
 #include <cmath>
 
 namespace nphm {
 namespace fit {
+
+struct BackwardPacks { tcl::PackedLinear l3, l2, l1; };
 
 constexpr int TM = 2;
 constexpr int P = 32 * TM;
@@ -54,7 +59,8 @@ struct Buffers {
     float *member_s;                // n x members
     const unsigned char *mask;      // optional n: 0 = the point is excluded from the loss (joint fitter: failed correspondences)
     float *grad_points;             // optional n x 3: d loss / d point (accumulated over members with atomics)
-    const float *acts;              // optional: hidden activations saved by the tensor-core forward, [member][tile128][feature][128]
+    float *acts;                    // optional: activation derivatives saved by the tensor-core forward, [member][rows][tc::kActLd];
+                                    // the backward GEMMs overwrite them with the layer deltas
     float *out, *S, *gsign;         // n each
     float *acc;                     // members x 2H   (sum delta0 | sum delta2)
     float *blend_acc;               // n_loc x 3
@@ -208,216 +214,154 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward pass from the activations saved by the tensor-core forward (b.acts), on warp-level tensor-core MMAs.
-// One CTA per (64-point tile, member).  delta_{l-1} = (delta_l W_l) * sigma'(h_{l-1}) is a (64 x n_l) x (n_l x n_{l-1})
-// product: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small, big*big + big*small + small*big), which keeps
-// fp32-level accuracy (the latent gradient is pinned to the reference's autograd at 2e-4 of its max).  Shared-memory
-// rows use a pitch of 72 floats: fragment loads (4 rows x 8 points per instruction) then hit 32 distinct banks.
-constexpr int PP = 72;
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward pass of the tensor-core path, layer by layer on tcgen05 (tc_linear.cu, batched over the members):
+//   the forward (tc::ensemble_tc_kernel_v8<.., ACTS>) leaves sigma'_l = d softplus / d pre-activation of every hidden unit, one row
+//   of tc::kActLd floats per (member, point);
+//   fit_upstream_kernel   g_s[m][p] = dL/d s_m(p) (blend + loss), blend-weight gradients w.r.t. anchors and points
+//   3 batched GEMMs       delta2 = sigma'2 * (sigma'3 (diag(w4) W3));  delta1 = sigma'1 * (delta2 W2[:, :N1]) / sqrt2;
+//                         delta0 = sigma'0 * (delta1 W1)      - per unit upstream gradient (times kDeltaScale), each written in
+//                         place over the sigma' block it consumes
+//   fit_reduce_kernel     per member: g_s-weighted column sums of delta0 / delta2 (-> acc), per point
+//                         g_s (W0x^T delta0 + W2x^T delta2 / sqrt2) (-> grad_points)
 
-__device__ __forceinline__ void tf32_split(float x, uint32_t &big, uint32_t &small)
+// per point: upstream gradient of every member output, blend-weight path of the anchor / point gradients
+__global__ void __launch_bounds__(256) fit_upstream_kernel(const Dims d, const Buffers b, float lambda_surface, float *__restrict__ gs,
+                                                           long long gs_stride)
 {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
-    const float r = x - __uint_as_float(big);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-// rows_out[j][p] <- scale * sigma'(rows_out[j][p]) * sum_n delta[n][p] * W[n*ldw + j]      (j < J, n < K, 64 points)
-__device__ __forceinline__ void mma_layer_bwd(const float *__restrict__ W, int ldw, int K, int J, float scale,
-                                              const float *delta, float *rows_out, int warp, int lane, int nwarps)
-{
-    const int g = lane >> 2, t = lane & 3;
-    const int n_tiles = (J + 7) / 8, k_steps = (K + 7) / 8;
-    for (int nt0 = warp; nt0 < n_tiles; nt0 += 2 * nwarps) {
-        const int nt1 = nt0 + nwarps;                       // second column tile of this warp (may not exist)
-        const bool two = nt1 < n_tiles;
-        float c[2][4][4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) c[u][mt][e] = 0.f;
-        const int j0 = nt0 * 8 + g, j1 = nt1 * 8 + g;
-#pragma unroll 2
-        for (int ks = 0; ks < k_steps; ++ks) {
-            const int ka = ks * 8 + t, kb = ka + 4;
-            uint32_t bb[2][2], bs[2][2];
-            {
-                const float w00 = (ka < K && j0 < J) ? __ldg(W + (size_t)ka * ldw + j0) : 0.f;
-                const float w01 = (kb < K && j0 < J) ? __ldg(W + (size_t)kb * ldw + j0) : 0.f;
-                tf32_split(w00, bb[0][0], bs[0][0]); tf32_split(w01, bb[0][1], bs[0][1]);
-                const float w10 = (two && ka < K && j1 < J) ? __ldg(W + (size_t)ka * ldw + j1) : 0.f;
-                const float w11 = (two && kb < K && j1 < J) ? __ldg(W + (size_t)kb * ldw + j1) : 0.f;
-                tf32_split(w10, bb[1][0], bs[1][0]); tf32_split(w11, bb[1][1], bs[1][1]);
-            }
-            const float *da = delta + (size_t)ka * PP, *db = delta + (size_t)kb * PP;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                const int p0 = mt * 16 + g;
-                const float a0 = ka < K ? da[p0] : 0.f, a1 = ka < K ? da[p0 + 8] : 0.f;
-                const float a2 = kb < K ? db[p0] : 0.f, a3 = kb < K ? db[p0 + 8] : 0.f;
-                uint32_t ab[4], as[4];
-                tf32_split(a0, ab[0], as[0]); tf32_split(a1, ab[1], as[1]);
-                tf32_split(a2, ab[2], as[2]); tf32_split(a3, ab[3], as[3]);
-                mma_tf32(c[0][mt], as, bb[0]); mma_tf32(c[0][mt], ab, bs[0]); mma_tf32(c[0][mt], ab, bb[0]);
-                if (two) { mma_tf32(c[1][mt], as, bb[1]); mma_tf32(c[1][mt], ab, bs[1]); mma_tf32(c[1][mt], ab, bb[1]); }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
-            const int jb = (u ? nt1 : nt0) * 8 + 2 * t;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = jb + (e & 1), pt = mt * 16 + g + ((e >> 1) << 3);
-                    if (j < J) {
-                        float *ptr = rows_out + (size_t)j * PP + pt;
-                        const float h = *ptr;
-                        const float sg = h > 0.2f ? 1.0f : -expm1f(-100.0f * h);
-                        *ptr = c[u][mt][e] * scale * sg;
-                    }
-                }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) fit_backward_mma_kernel(const Dims d, const Weights w, const Buffers b,
-                                                                      float lambda_surface)
-{
-    extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads / 32;
-    const int m = blockIdx.y;
-    const long long p0 = (long long)blockIdx.x * P;
-    const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
-    const bool has_anchor = m < d.n_loc;
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    if (has_anchor) { ax = b.anchors[m * 3]; ay = b.anchors[m * 3 + 1]; az = b.anchors[m * 3 + 2]; }
-    // rows: h0 [0,H) | h1 [H, H+N1) | h2 | h3 | g_s (1 row) | d loss / d x (3 rows, only with grad_points)
-    float *rh0 = sm, *rh1 = rh0 + (size_t)d.H * PP, *rh2 = rh1 + (size_t)d.N1 * PP, *rh3 = rh2 + (size_t)d.H * PP;
-    float *rg = rh3 + (size_t)d.H * PP;
-    {
-        const int n_feat = 3 * d.H + d.N1;
-        const long long tiles128 = (b.n + 127) / 128;
-        const float *src = b.acts + ((size_t)m * tiles128 + (blockIdx.x >> 1)) * n_feat * 128 + (blockIdx.x & 1) * P;
-        for (int f = warp; f < n_feat; f += nwarps) {
-            const float2 v = *reinterpret_cast<const float2 *>(src + (size_t)f * 128 + lane * 2);
-            *reinterpret_cast<float2 *>(sm + (size_t)f * PP + lane * 2) = v;
-        }
-    }
-    // upstream gradient of this member's output per point, blend-path anchor gradient (same math as fit_member_kernel)
-    if (warp == 0) {
+    __shared__ float s_anch[64 * 3], s_acc[64 * 3];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < d.n_loc * 3; i += blockDim.x) { s_anch[i] = b.anchors[i]; s_acc[i] = 0.f; }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < b.n;
+    float x = 0.f, y = 0.f, z = 0.f, g_out = 0.f, Sp = 1.f, outv = 0.f;
+    if (ok) {
         const float inv_count = b.stats[0] > 0.f ? 1.0f / b.stats[0] : 0.f;
-        float ba[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const long long idx = p0 + lane * 2 + i;
-            float gs = 0.f;
-            float gxb[3] = {0.f, 0.f, 0.f};
-            if (idx < b.n) {
-                const float x = b.points[idx * 3], y = b.points[idx * 3 + 1], z = b.points[idx * 3 + 2];
-                const float g_out = lambda_surface * b.gsign[idx] * inv_count;
-                const float Sp = b.S[idx] + 1e-6f;
-                float dd, r = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
-                if (has_anchor) {
-                    dx = ax - x; dy = ay - y; dz = az - z;
-                    r = sqrtf(dx * dx + dy * dy + dz * dz);
-                    const float nrm = r + 10e-6f;
-                    dd = -(nrm * nrm);
-                } else {
-                    dd = -0.2f;
-                }
-                const float wk = expf(__fdiv_rn(dd, 0.01f));
-                gs = g_out * wk / Sp;
-                if (has_anchor && r > 0.f) {
-                    const float s_k = b.member_s[idx * d.n_members + m];
-                    const float g_w = g_out * (s_k - b.out[idx]) / Sp;
-                    const float coef = g_w * wk * (1.0f / 0.01f) * (-2.0f) * (r + 10e-6f) / r;
-                    ba[0] += coef * dx; ba[1] += coef * dy; ba[2] += coef * dz;
-                    gxb[0] = -coef * dx; gxb[1] = -coef * dy; gxb[2] = -coef * dz;     // d w_k / d x = - d w_k / d a_k
-                }
+        x = b.points[idx * 3]; y = b.points[idx * 3 + 1]; z = b.points[idx * 3 + 2];
+        g_out = lambda_surface * b.gsign[idx] * inv_count;
+        Sp = b.S[idx] + 1e-6f;
+        outv = b.out[idx];
+    }
+    float gx[3] = {0.f, 0.f, 0.f};
+    for (int m = 0; m < d.n_members; ++m) {
+        const bool has_anchor = m < d.n_loc;
+        float c[3] = {0.f, 0.f, 0.f}, gsv = 0.f;
+        if (ok) {
+            float dd, r = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            if (has_anchor) {
+                dx = s_anch[m * 3] - x; dy = s_anch[m * 3 + 1] - y; dz = s_anch[m * 3 + 2] - z;
+                r = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float nrm = r + 10e-6f;
+                dd = -(nrm * nrm);
+            } else {
+                dd = -0.2f;
             }
-            rg[lane * 2 + i] = gs;
-            if (b.grad_points) {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) rg[PP * (1 + a) + lane * 2 + i] = gxb[a];
+            const float wk = expf(__fdiv_rn(dd, 0.01f));
+            gsv = g_out * wk / Sp;
+            if (has_anchor && r > 0.f) {
+                const float s_k = b.member_s[idx * d.n_members + m];
+                const float g_w = g_out * (s_k - outv) / Sp;
+                const float coef = g_w * wk * (1.0f / 0.01f) * (-2.0f) * (r + 10e-6f) / r;
+                c[0] = coef * dx; c[1] = coef * dy; c[2] = coef * dz;
+                gx[0] -= c[0]; gx[1] -= c[1]; gx[2] -= c[2];                  // d w_k / d x = - d w_k / d a_k
             }
+            gs[(size_t)m * gs_stride + idx] = gsv;
         }
         if (has_anchor) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                float v = ba[a];
+                float v = c[a];
 #pragma unroll
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0 && v != 0.f) atomicAdd(b.blend_acc + m * 3 + a, v);
+                if (lane == 0 && v != 0.f) atomicAdd(&s_acc[m * 3 + a], v);
             }
         }
     }
+    if (ok && b.grad_points) { b.grad_points[idx * 3] = gx[0]; b.grad_points[idx * 3 + 1] = gx[1]; b.grad_points[idx * 3 + 2] = gx[2]; }
     __syncthreads();
-    // delta3 = g_s * w4 * sigma'(h3), in place over h3
-    {
-        const float *W4 = w.W[4] + (size_t)set * d.H;
-        const float2 gs = *reinterpret_cast<const float2 *>(rg + lane * 2);
-        for (int n = warp; n < d.H; n += nwarps) {
-            float2 *ptr = reinterpret_cast<float2 *>(rh3 + (size_t)n * PP + lane * 2);
-            const float2 h = *ptr;
-            const float w4 = __ldg(W4 + n);
-            float2 o;
-            o.x = gs.x * w4 * (h.x > 0.2f ? 1.0f : -expm1f(-100.0f * h.x));
-            o.y = gs.y * w4 * (h.y > 0.2f ? 1.0f : -expm1f(-100.0f * h.y));
-            *ptr = o;
-        }
-    }
+    for (int i = threadIdx.x; i < d.n_loc * 3; i += blockDim.x)
+        if (s_acc[i] != 0.f) atomicAdd(b.blend_acc + i, s_acc[i]);
+}
+
+// warp per (member, point) row of the delta blocks: column sums of delta0 / delta2 and (POINTS) the gradient w.r.t. the point
+// through the member's local coordinates.  grid (ceil(n / kReduceRows), members), kReduceRows rows per CTA.
+constexpr int kReduceRows = 128, kReduceWarps = 8;
+constexpr float kDeltaScale = 64.0f;          // the GEMMs carry the deltas per unit upstream gradient, times this power of two: the
+                                              // fp16 hi/lo operand split needs O(1) magnitudes (g_s itself is ~1e-4 / n_points)
+template <bool POINTS>
+__global__ void __launch_bounds__(32 * kReduceWarps) fit_reduce_kernel(const Dims d, const Weights w, const Buffers b,
+                                                                      const float *__restrict__ deltas, long long rows_per_member,
+                                                                      const float *__restrict__ gs)
+{
+    constexpr int kCols = 7;                                  // columns per lane: lane + 32 i  (H <= 224)
+    __shared__ float s_sum[2 * 224];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.y;
+    const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
+    const bool mirror = (m & 1) && m < 2 * d.n_symm;
+    for (int i = threadIdx.x; i < 2 * 224; i += blockDim.x) s_sum[i] = 0.f;
     __syncthreads();
-    mma_layer_bwd(w.W[3] + (size_t)set * d.H * d.H, d.H, d.H, d.H, 1.0f, rh3, rh2, warp, lane, nwarps);                    // delta2
-    __syncthreads();
-    mma_layer_bwd(w.W[2] + (size_t)set * d.H * d.H, d.H, d.H, d.N1, 0.70710678118654752f, rh2, rh1, warp, lane, nwarps);   // delta1
-    __syncthreads();
-    mma_layer_bwd(w.W[1] + (size_t)set * d.N1 * d.H, d.H, d.N1, d.H, 1.0f, rh1, rh0, warp, lane, nwarps);                   // delta0
-    __syncthreads();
-    if (b.grad_points) {
-        // d loss / d x_p through this member's local coordinates: g_c(p) = W0x^T delta0(p) + W2x^T delta2(p) / sqrt2
-        // (x component negated for mirrored members), plus the blend-weight path stored above.  8 threads per point.
-        const int pt = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float w0[kCols][3], w2[kCols][3];
+    if (POINTS) {
         const int in0 = 3 + d.C;
         const float *W0 = w.W[0] + (size_t)set * d.H * in0;
         const float *W2 = w.W[2] + (size_t)set * d.H * d.H + d.N1;
-        const int per = (d.H + 7) / 8;
-        float g[3] = {0.f, 0.f, 0.f};
-        for (int n = part * per; n < min(d.H, (part + 1) * per); ++n) {
-            const float d0 = rh0[(size_t)n * PP + pt], d2 = 0.70710678118654752f * rh2[(size_t)n * PP + pt];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-                g[a] = fmaf(__ldg(W0 + (size_t)n * in0 + a), d0, fmaf(__ldg(W2 + (size_t)n * d.H + a), d2, g[a]));
-        }
-        const bool mirror = (m & 1) && m < 2 * d.n_symm;
-        if (mirror) g[0] = -g[0];
+        for (int i = 0; i < kCols; ++i) {
+            const int j = lane + 32 * i;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) atomicAdd(rg + PP * (1 + a) + pt, g[a]);
-        __syncthreads();
-        if (threadIdx.x < 3 * P) {
-            const int a = threadIdx.x / P, q = threadIdx.x % P;
-            const long long idx = p0 + q;
-            const float v = rg[PP * (1 + a) + q];
-            if (idx < b.n && v != 0.f) atomicAdd(b.grad_points + idx * 3 + a, v);
+            for (int a = 0; a < 3; ++a) {
+                w0[i][a] = j < d.H ? __ldg(W0 + (size_t)j * in0 + a) : 0.f;
+                w2[i][a] = j < d.H ? 0.70710678118654752f * __ldg(W2 + (size_t)j * d.H + a) : 0.f;
+            }
         }
     }
-    float *acc = b.acc + (size_t)m * 2 * d.H;
-    for (int n = warp; n < 2 * d.H; n += nwarps) {
-        const float *row = (n < d.H ? rh0 + (size_t)n * PP : rh2 + (size_t)(n - d.H) * PP) + lane * 2;
-        const float2 v = *reinterpret_cast<const float2 *>(row);
-        float s2 = v.x + v.y;
+    float c0[kCols], c2[kCols];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        if (lane == 0 && s2 != 0.f) atomicAdd(acc + n, s2);
+    for (int i = 0; i < kCols; ++i) { c0[i] = 0.f; c2[i] = 0.f; }
+    const long long r_begin = (long long)blockIdx.x * kReduceRows;
+    for (int rr = warp; rr < kReduceRows; rr += kReduceWarps) {
+        const long long row = r_begin + rr;
+        if (row >= b.n) break;
+        const float *src = deltas + ((size_t)m * rows_per_member + row) * tc::kActLd;
+        const float up = gs[(size_t)m * rows_per_member + row] * (1.0f / kDeltaScale);      // upstream gradient of s_m(row)
+        if (up == 0.f) continue;
+        float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) {
+            const int j = lane + 32 * i;
+            const float d0 = j < d.H ? up * src[tc::kActOff0 + j] : 0.f;
+            const float d2 = j < d.H ? up * src[tc::kActOff2 + j] : 0.f;
+            c0[i] += d0; c2[i] += d2;
+            if (POINTS) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) g[a] = fmaf(w0[i][a], d0, fmaf(w2[i][a], d2, g[a]));
+            }
+        }
+        if (POINTS) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int o = 16; o; o >>= 1) g[a] += __shfl_xor_sync(0xffffffffu, g[a], o);
+            }
+            if (mirror) g[0] = -g[0];
+            if (lane < 3) {
+                const float v = lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]);
+                if (v != 0.f) atomicAdd(b.grad_points + row * 3 + lane, v);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+        const int j = lane + 32 * i;
+        if (j < d.H) { atomicAdd(&s_sum[j], c0[i]); atomicAdd(&s_sum[224 + j], c2[i]); }
+    }
+    __syncthreads();
+    float *acc = b.acc + (size_t)m * 2 * d.H;
+    for (int i = threadIdx.x; i < 2 * d.H; i += blockDim.x) {
+        const float v = i < d.H ? s_sum[i] : s_sum[224 + i - d.H];
+        if (v != 0.f) atomicAdd(acc + i, v);
     }
 }
 
@@ -624,13 +568,44 @@ __global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const W
 
 using namespace nphm;
 
+namespace nphm { namespace fit {
+// adjoint weights of the three hidden layers, one packed set per weight set of the ensemble (built on first use)
+int backward_packs(nphm_ensemble *h, cudaStream_t stream)
+{
+    if (h->fit_packs) return NPHM_OK;
+    const int H = h->cfg.hidden_dim, N1 = h->dims.N[1], sets = h->n_members - h->cfg.n_symm_pairs;
+    BackwardPacks *bp = new BackwardPacks();
+    int rc;
+    // delta2_pre[p][j] = sum_f sigma'3[p][f] w4[f] W3[f][j]       (w4 folded into the rows of W3)
+    if ((rc = bp->l3.pack(h->weights.W[3].as<float>(), H, H, H, 0, 0, true, kDeltaScale, stream, sets, (long long)H * H,
+                          h->weights.W[4].as<float>(), H)) ||
+        // delta1_pre[p][j] = sum_n delta2[p][n] W2[n][j] / sqrt2,  j < N1
+        (rc = bp->l2.pack(h->weights.W[2].as<float>(), H, N1, H, 0, 0, true, 0.70710678118654752f, stream, sets, (long long)H * H)) ||
+        // delta0_pre[p][j] = sum_n delta1[p][n] W1[n][j],           n < N1
+        (rc = bp->l1.pack(h->weights.W[1].as<float>(), H, H, N1, 0, 0, true, 1.0f, stream, sets, (long long)N1 * H))) {
+        delete bp;
+        return rc;
+    }
+    h->fit_packs = bp;
+    return NPHM_OK;
+}
+}}
+namespace nphm {
+void fit_packs_destroy(nphm_ensemble *h)
+{
+    delete h->fit_packs;
+    h->fit_packs = nullptr;
+}
+}
+
 extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long n_points)
 {
     if (!h || n_points < 0) return -1;
     long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
                        (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
-    // hidden activations handed from the tensor-core forward to the backward kernel: [member][128-point tile][feature][128]
-    floats += (long long)h->n_members * ((n_points + 127) / 128) * (3 * h->cfg.hidden_dim + h->dims.N[1]) * 128;
+    // activation derivatives handed from the tensor-core forward to the backward GEMMs ([member][rows][kActLd], rows padded to the
+    // 128-point tile) and the upstream gradient of every member output ([member][rows])
+    floats += (long long)h->n_members * ((n_points + 127) / 128) * 128 * (nphm::tc::kActLd + 1);
     return floats * 4 + 1024;
 }
 
@@ -693,7 +668,6 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
     b.upstream = upstream_dev;
     b.sdf_out = sdf_out_dev;
     b.grad_points = grad_points_dev;
-    if (grad_points_dev) NPHM_CUDA_CHECK(cudaMemsetAsync(grad_points_dev, 0, (size_t)n_points * 3 * sizeof(float), stream));
 
     const int tiles = (int)ceil_div(n_points, fit::P);
     dim3 grid(tiles, h->n_members);
@@ -716,10 +690,28 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
     fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
     NPHM_CUDA_CHECK(cudaGetLastError());
     if (b.acts) {
-        const size_t bsm = (size_t)(3 * d.H + d.N1 + 4) * fit::PP * sizeof(float);
-        NPHM_REQUIRE(bsm <= 227 * 1024, "nphm_fit_identity_step: hidden width %d too large for the backward kernel", d.H);
-        NPHM_CUDA_CHECK(cudaFuncSetAttribute(fit::fit_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-        fit::fit_backward_mma_kernel<<<grid, fit::kThreads, bsm, stream>>>(d, w, b, fp->lambda_surface);
+        const long long rows = ceil_div(n_points, 128) * 128;
+        float *gs = acts + (size_t)h->n_members * rows * tc::kActLd;
+        if ((rc = fit::backward_packs(h, stream))) return rc;
+        const fit::BackwardPacks &bp = *h->fit_packs;
+        fit::fit_upstream_kernel<<<(unsigned)ceil_div(n_points, 256), 256, 0, stream>>>(d, b, fp->lambda_surface, gs, rows);
+        NPHM_CUDA_CHECK(cudaGetLastError());
+        tcl::LinearParams lp{};
+        lp.M = n_points; lp.mode = tcl::kModeMult; lp.batch = h->n_members; lp.w_pairs = d.n_symm;
+        lp.lda1 = lp.ldmul = lp.ldc = tc::kActLd;
+        lp.sA1 = lp.sMul = lp.sC = rows * tc::kActLd;
+        // delta2 (over sigma'2): A = sigma'3
+        lp.A1 = acts + tc::kActOff3; lp.K1 = d.H; lp.Mul = acts + tc::kActOff2; lp.C = acts + tc::kActOff2;
+        if ((rc = tcl::launch_linear(bp.l3, lp, stream))) return rc;
+        // delta1 (over sigma'1)
+        lp.A1 = acts + tc::kActOff2; lp.K1 = d.H; lp.Mul = acts + tc::kActOff1; lp.C = acts + tc::kActOff1;
+        if ((rc = tcl::launch_linear(bp.l2, lp, stream))) return rc;
+        // delta0 (over sigma'0)
+        lp.A1 = acts + tc::kActOff1; lp.K1 = d.N1; lp.Mul = acts + tc::kActOff0; lp.C = acts + tc::kActOff0;
+        if ((rc = tcl::launch_linear(bp.l1, lp, stream))) return rc;
+        dim3 rgrid((unsigned)ceil_div(n_points, fit::kReduceRows), h->n_members);
+        if (grad_points_dev) fit::fit_reduce_kernel<true><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows, gs);
+        else fit::fit_reduce_kernel<false><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows, gs);
     } else {
         if (grad_points_dev) {
             set_error("gradient w.r.t. the points needs the tensor-core configuration (hidden 200, 4 layers, condition 96)");

@@ -32,7 +32,8 @@ constexpr int kColD1 = 112, kColA1Hi = 0, kColA1Lo = 56;
 constexpr int kColD2 = 304, kColA2Hi = 0, kColA2Lo = 104;
 constexpr int kColD3 = 208;
 constexpr int kRecSlots = 3;
-constexpr int kActFeat = kH + kN1 + kH + kH;      // features saved per point for the fitting backward: h0 | h1 | h2 | h3
+// activation derivatives saved per (member, point) for the fitting backward: sigma'0 [208] | sigma'1 [112] | sigma'2 [208] | sigma'3 [208]
+constexpr int kActOff0 = 0, kActOff1 = 208, kActOff2 = 320, kActOff3 = 528, kActLd = 736;
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
 constexpr int kRecB1 = 832;        // 112
@@ -57,7 +58,7 @@ struct Params {
     long long quirk_period;
     float *out;
     float *members_out;         // optional [n_queries][n_points][n_members]: un-blended member outputs s_k (fitting)
-    float *acts_out;            // optional [n_members][tiles][kActFeat][128]: hidden activations h0|h1|h2|h3 (fitting backward)
+    float *acts_out;            // optional [n_members][tiles * 128][kActLd]: activation derivatives (fitting backward)
     int n_members, n_symm;
     // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
     const float *anchors;       // [n_queries][n_members-1][3]

@@ -427,14 +427,23 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 mask = mq[0] | mq[1] | mq[2] | mq[3];
             }
 
-            // hidden activations for the fitting backward (h = v / S), feature-major so that a warp store is one 128-byte line
-            auto save_half = [&](float *ab, int f0, int n_real, const float (&v)[8]) {
+            // for the fitting backward: the derivative of every hidden activation, sigma'(pre) = 1 - 2^(-softplus) (v is the
+            // softplus in log2 units), one row of kActLd floats per (member, point) - the operand layout of the layer-wise
+            // backward GEMMs (fit.cu).  Columns beyond a layer's width receive don't-care values.
+            auto save_half = [&](float *ab, int col0, const float (&v)[8]) {
+                float s[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (e < n_real) ab[(size_t)(f0 + e) * 128 + row] = v[e] * (1.0f / kS);
+                for (int e = 0; e < 8; ++e) {
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-v[e]));
+                    s[e] = 1.0f - ex;
+                }
+                reinterpret_cast<float4 *>(ab + col0)[0] = make_float4(s[0], s[1], s[2], s[3]);
+                reinterpret_cast<float4 *>(ab + col0)[1] = make_float4(s[4], s[5], s[6], s[7]);
             };
             auto acts_of = [&](int member) -> float * {
-                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query + (tile % tiles_per_query)) * kActFeat * 128 : nullptr;
+                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query * 128 + (size_t)(tile % tiles_per_query) * 128 + row) * kActLd
+                            : nullptr;
             };
             auto publish = [&](uint64_t *bar) {          // my TMEM stores are visible to the MMA issuer after this
                 tc_wait_st();
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                             v[e] = sp_sel(t, e);
                         }
                     }
-                    if (ACTS) save_half(ab, 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+                    if (ACTS) save_half(ab, kActOff0 + 16 * u + 8 * h, v);
                     store_half(col, h, v);
                 }
             };
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             auto layer3_dot = [&](auto tU0, auto tN, auto tOff, const float *r, float *ab, float acc) -> float {
                 tmem_phase(tU0, tN, tOff, IC<kUnits208 - 1>(), kColQ, nullptr, [&](int u, int h, const float (&v)[8]) {
                     if (u == kUnits208 - 1 && h == 1) return;          // padding: w4 is zero there
-                    if (ACTS) save_half(ab, 2 * kH + kN1 + 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+                    if (ACTS) save_half(ab, kActOff3 + 16 * u + 8 * h, v);
 #pragma unroll
                     for (int i4 = 0; i4 < 2; ++i4) {
                         const float4 w = *reinterpret_cast<const float4 *>(r + kRecW4 + 16 * u + 8 * h + 4 * i4);     // w4 pad = 0
@@ -613,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                         if (h == 0) { v[5] = cx; v[6] = cy; v[7] = cz; }
                         else v[0] = 1.0f;
                     }
-                    if (ACTS) save_half(ab, kH + 16 * u + 8 * h, kN1 - 16 * u - 8 * h, v);
+                    if (ACTS) save_half(ab, kActOff1 + 16 * u + 8 * h, v);
                     store_half(tl + kColQ + 16 * u, h, v);
                 });
                 TRACE_EVT(trw, m, tr0 + 4);
@@ -645,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 TRACE_EVT(trw, m, tr0 + 5);
                 tmem_phase(IC<0>(), IC<kUnits208>(), IC<kOffE2>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready, [&](int u, int h, float (&v)[8]) {
                     if (u == kUnits208 - 1 && h == 1) v[0] = 1.0f;          // k = 200: bias row of layer 3
-                    if (ACTS) save_half(ab, kH + kN1 + 16 * u + 8 * h, kH - 16 * u - 8 * h, v);
+                    if (ACTS) save_half(ab, kActOff2 + 16 * u + 8 * h, v);
                     store_half(tl + kColP + 16 * u, h, v);
                 });
                 TRACE_EVT(trw, m, tr0 + 6);

@@ -25,23 +25,24 @@ namespace nphm {
 namespace tcl {
 using namespace tc;
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;                   // operand ring: 4 stages, 3 when two CTAs are to share an SM (batched launches)
+constexpr int kARing = 4;                       // fp32 staging ring of A (independent of the operand ring)
 constexpr int kRowWarps = 4;
 constexpr int kThreads = 32 * (kRowWarps + 2);
 constexpr int kMaxNt = 256;
 
-struct __align__(128) Stage {
-    uint8_t a_hi[128 * 32], a_lo[128 * 32];      // 128 rows x 16 fp16, core-matrix order
-    uint8_t b[kMaxNt * 64];                      // Nt x 16 hi | Nt x 16 lo
-};
 constexpr int kAPitch = 20;                      // floats per staged fp32 row (16 + 4: 80-byte pitch spreads the banks)
 constexpr int kADepth = 3;                       // k-steps of A kept in flight per thread (cp.async groups)
-struct __align__(128) Smem {
-    Stage st[kStages];
-    float a32[kStages][128][kAPitch];            // fp32 staging of A: every thread copies (cp.async) and reads ITS OWN row
-    uint64_t a_full[kStages], b_full[kStages], empty[kStages], d_ready;
+// dynamic shared memory: [Ctl | stages x (a_hi 4 KB | a_lo 4 KB | b Nt*64) | a32 ring]
+struct __align__(128) Ctl {
+    uint64_t a_full[kMaxStages], b_full[kMaxStages], empty[kMaxStages], d_ready;
     uint32_t tmem_base;
 };
+constexpr int kCtlBytes = 128;
+static_assert(sizeof(Ctl) <= kCtlBytes, "control block");
+constexpr int kA32Bytes = kARing * 128 * kAPitch * 4;
+__host__ __device__ inline int stage_bytes(int Nt) { return 2 * 128 * 32 + Nt * 64; }
+inline int smem_bytes(int Nt, int stages) { return kCtlBytes + stages * stage_bytes(Nt) + kA32Bytes; }
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -60,10 +61,19 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    Ctl &sm = *reinterpret_cast<Ctl *>(smem_raw);
+    const int kStages = p.stages;
+    const int st_bytes = stage_bytes(p.Nt);
+    uint8_t *const st0 = smem_raw + kCtlBytes;
+    auto st_a_hi = [&](int s) { return st0 + (size_t)s * st_bytes; };
+    auto st_a_lo = [&](int s) { return st0 + (size_t)s * st_bytes + 128 * 32; };
+    auto st_b = [&](int s) { return st0 + (size_t)s * st_bytes + 2 * 128 * 32; };
+    float (*a32)[128][kAPitch] = reinterpret_cast<float (*)[128][kAPitch]>(st0 + (size_t)kStages * st_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row0 = (long long)blockIdx.x * 128;
     const int nt_idx = blockIdx.y;
+    const int z = blockIdx.z;                             // batch entry: own A / C / Mul / row scale, weights of set(z)
+    const int wset = z < 2 * p.w_pairs ? (z >> 1) : z - p.w_pairs;
     const int n0 = nt_idx * p.Nt;
     const uint32_t tmem_cols = p.Nt <= 32 ? 32 : (p.Nt <= 64 ? 64 : (p.Nt <= 128 ? 128 : 256));
 
@@ -86,12 +96,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
     if (warp == kRowWarps) {
         // ================================================================ producer: weight slabs (bulk async copies)
         if (lane == 0) {
-            const uint8_t *w = p.W + (size_t)nt_idx * p.ksteps * slab_bytes;
+            const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
             for (int j = 0; j < p.ksteps; ++j) {
                 const int s = j % kStages;
                 mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
                 mbar_expect_tx(&sm.b_full[s], slab_bytes);
-                bulk_g2s(sm.st[s].b, w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
+                bulk_g2s(st_b(s), w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
             }
         }
     } else if (warp == kRowWarps + 1) {
@@ -105,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             mbar_wait(&sm.b_full[s], ph);
             tc_fence_after();
             if (leader) {
-                const uint64_t a_hi = make_desc(smem_u32(sm.st[s].a_hi), 128, 256), a_lo = make_desc(smem_u32(sm.st[s].a_lo), 128, 256);
-                const uint64_t b_hi = make_desc(smem_u32(sm.st[s].b), 128, 256);
+                const uint64_t a_hi = make_desc(smem_u32(st_a_hi(s)), 128, 256), a_lo = make_desc(smem_u32(st_a_lo(s)), 128, 256);
+                const uint64_t b_hi = make_desc(smem_u32(st_b(s)), 128, 256);
                 const uint64_t b_lo = b_hi + (uint64_t)(p.Nt * 2);          // lo half: Nt * 32 bytes further
                 tc_mma_ss(tmem, a_hi, b_hi, idesc, j == 0 ? 0 : 1);
                 tc_mma_ss(tmem, a_hi, b_lo, idesc, 1);
@@ -121,10 +131,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         const int t = threadIdx.x;                        // row of the tile = TMEM lane
         const long long row = row0 + t;
         const bool row_ok = row < p.M;
-        const float *a1 = p.A1 ? p.A1 + (size_t)(row_ok ? row : 0) * p.lda1 : nullptr;
+        const float *a1 = p.A1 ? p.A1 + (size_t)z * p.sA1 + (size_t)(row_ok ? row : 0) * p.lda1 : nullptr;
         const float *a2 = (p.A2 && !p.a2_onehot) ? p.A2 + (size_t)(row_ok ? row : 0) * p.lda2 : nullptr;
         const int hot = p.a2_onehot ? (int)(row % p.K2) : -1;
-        const bool vec_ok = p.A1 && (p.lda1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0);
+        const bool vec_ok = p.A1 && (p.lda1 % 4 == 0) && (p.sA1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0);
         const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16;     // (row/8)*256 + (row%8)*16, + 128 for kk >= 8
         // the 16 inputs of k-step j: cols [16 j, 16 j + 16) of [A1 | A2], zero beyond the real width / the last row
         auto load_step = [&](int j, float (&v)[16]) {
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         auto fast = [&](int j) { return row_ok && vec_ok && 16 * j + 16 <= p.K1; };
         auto prefetch = [&](int j) {
             if (j < p.ksteps && fast(j)) {
-                const uint32_t dst = smem_u32(&sm.a32[j % kStages][t][0]);
+                const uint32_t dst = smem_u32(&a32[j % kARing][t][0]);
                 const float *src = a1 + 16 * j;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -164,13 +174,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         };
         for (int d = 0; d < kADepth; ++d) prefetch(d);
         for (int j = 0; j < p.ksteps; ++j) {
-            const int s = j % kStages;
+            const int s = j % kStages, sa = j % kARing;
             float cur[16];
             asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
             if (fast(j)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 f = *reinterpret_cast<const float4 *>(&sm.a32[s][t][4 * i]);
+                    const float4 f = *reinterpret_cast<const float4 *>(&a32[sa][t][4 * i]);
                     cur[4 * i] = f.x; cur[4 * i + 1] = f.y; cur[4 * i + 2] = f.z; cur[4 * i + 3] = f.w;
                 }
             } else {
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
 #pragma unroll
             for (int i = 0; i < 8; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
             mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
-            uint8_t *ah = sm.st[s].a_hi + off0, *al = sm.st[s].a_lo + off0;
+            uint8_t *ah = st_a_hi(s) + off0, *al = st_a_lo(s) + off0;
             *reinterpret_cast<uint4 *>(ah) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(ah + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             *reinterpret_cast<uint4 *>(al) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -196,7 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         tc_fence_after();
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
         const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
-        const float *mul = p.Mul ? p.Mul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul : nullptr;
+        const float *mul = p.Mul ? p.Mul + (size_t)z * p.sMul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul : nullptr;
+        const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
+        float *const Cz = p.C + (size_t)z * p.sC;
         for (int c0 = 0; c0 < p.Nt; c0 += 16) {
             uint32_t r[16];
             tc_ld16(tl + c0, r);
@@ -210,12 +222,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 if (src && full && (lds % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(src + n0 + c0) + i);
+                        const float4 f = reinterpret_cast<const float4 *>(src + n0 + c0)[i];      // plain loads: C may alias Mul
                         aux[4 * i] = f.x; aux[4 * i + 1] = f.y; aux[4 * i + 2] = f.z; aux[4 * i + 3] = f.w;
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? __ldg(src + n0 + c0 + e) : 0.f;
+                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? src[n0 + c0 + e] : 0.f;
                 }
             }
 #pragma unroll
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 float x = __uint_as_float(r[e]);
                 dv[e] = 0.f;
                 if (n < p.N) {
-                    if (p.mode == kModeMult) x *= aux[e];
+                    if (p.mode == kModeMult) x *= aux[e] * rscale;
                     else {
                         x += aux[e];
                         if (p.mode == kModeSoftplus) {
@@ -240,8 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 }
                 o[e] = x;
             }
-            float *crow = p.C + (size_t)row * p.ldc + n0 + c0;
-            if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+            float *crow = Cz + (size_t)row * p.ldc + n0 + c0;
+            if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     reinterpret_cast<float4 *>(crow)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -275,7 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
 // W [rows x ldw] fp32 (reference layout [out][in]) -> slabs.  B[n][k] = scale * (transpose ? W[k0 + k][n0w + n] : W[n0w + n][k0 + k])
 // for n < N, k < K, zero elsewhere; n tiles of Nt, k-steps of 16; per slab Nt x 16 hi then Nt x 16 lo in core-matrix order.
 __global__ void pack_linear_kernel(const float *__restrict__ W, int ldw, int N, int K, int n_off, int k_off, int transpose,
-                                   float scale, int Nt, int n_tiles, int ksteps, uint8_t *__restrict__ out)
+                                   float scale, const float *__restrict__ k_scale, int Nt, int n_tiles, int ksteps,
+                                   uint8_t *__restrict__ out)
 {
     const size_t total = (size_t)n_tiles * ksteps * Nt * 16;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -285,7 +298,10 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, int ldw, int N, 
         const int tile = (int)(t / (16 * (size_t)Nt * ksteps));
         const int n = tile * Nt + nn, k = j * 16 + kk;
         float v = 0.f;
-        if (n < N && k < K) v = scale * (transpose ? W[(size_t)(k_off + k) * ldw + n_off + n] : W[(size_t)(n_off + n) * ldw + k_off + k]);
+        if (n < N && k < K) {
+            v = scale * (transpose ? W[(size_t)(k_off + k) * ldw + n_off + n] : W[(size_t)(n_off + n) * ldw + k_off + k]);
+            if (k_scale) v *= k_scale[k];
+        }
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
         const size_t off = (size_t)(nn >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
@@ -303,17 +319,22 @@ int choose_nt(int N)
 }
 
 int PackedLinear::pack(const float *W_dev, int ldw, int N_, int K_, int n_off, int k_off, bool transpose, float scale,
-                       cudaStream_t stream)
+                       cudaStream_t stream, int sets_, long long w_set_stride, const float *k_scale_dev, long long k_scale_stride)
 {
     N = N_; K = K_;
     Nt = choose_nt(N);
     n_tiles = (N + Nt - 1) / Nt;
     ksteps = (K + 15) / 16;
+    sets = sets_ > 0 ? sets_ : 1;
+    set_bytes = (size_t)n_tiles * ksteps * Nt * 64;
     int rc;
-    if ((rc = slabs.reserve((size_t)n_tiles * ksteps * Nt * 64))) return rc;
-    pack_linear_kernel<<<256, 256, 0, stream>>>(W_dev, ldw, N, K, n_off, k_off, transpose ? 1 : 0, scale, Nt, n_tiles, ksteps,
-                                                slabs.as<uint8_t>());
-    NPHM_CUDA_CHECK(cudaGetLastError());
+    if ((rc = slabs.reserve(set_bytes * sets))) return rc;
+    for (int s = 0; s < sets; ++s) {
+        pack_linear_kernel<<<64, 256, 0, stream>>>(W_dev + (size_t)s * w_set_stride, ldw, N, K, n_off, k_off, transpose ? 1 : 0, scale,
+                                                   k_scale_dev ? k_scale_dev + (size_t)s * k_scale_stride : nullptr, Nt, n_tiles,
+                                                   ksteps, slabs.as<uint8_t>() + (size_t)s * set_bytes);
+        NPHM_CUDA_CHECK(cudaGetLastError());
+    }
     return NPHM_OK;
 }
 
@@ -322,13 +343,24 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
     NPHM_REQUIRE(w.slabs.ptr && p.C && p.M > 0, "tc_linear: unpacked weights or NULL output");
     NPHM_REQUIRE(p.K1 + p.K2 == w.K, "tc_linear: input width %d + %d does not match the packed weights (%d)", p.K1, p.K2, w.K);
     NPHM_REQUIRE(p.mode != kModeMult || (p.Mul && p.mul_div > 0), "tc_linear: multiplier missing");
+    NPHM_REQUIRE(p.batch >= 1 && (p.batch == 1 || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot)),
+                 "tc_linear: batched launches support the plain and the multiplier epilogue only");
+    if (p.batch > 1) {
+        const int last = p.batch - 1, need = (last < 2 * p.w_pairs ? (last >> 1) : last - p.w_pairs) + 1;
+        NPHM_REQUIRE(need <= w.sets, "tc_linear: batch of %d needs %d weight sets, %d packed", p.batch, need, w.sets);
+    }
     p.W = w.slabs.as<uint8_t>();
+    p.w_stride = (long long)w.set_bytes;
     p.N = w.N; p.Nt = w.Nt; p.ksteps = w.ksteps;
     if (p.rows_per_bias <= 0) p.rows_per_bias = p.M;
     if (p.mul_div <= 0) p.mul_div = 1;
-    const int smem = (int)sizeof(Smem);
-    NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)w.n_tiles);
+    // three operand stages leave room for two CTAs per SM (the epilogue of one overlaps the main loop of the other); wide tiles
+    // and single launches of few tiles keep four
+    p.stages = (smem_bytes(p.Nt, 3) <= 112 * 1024 && ceil_div(p.M, 128) * w.n_tiles * p.batch > 148) ? 3 : kMaxStages;
+    const int smem = smem_bytes(p.Nt, p.stages);
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes(kMaxNt, kMaxStages)));
+    dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)w.n_tiles, (unsigned)p.batch);
     linear_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;

@@ -18,15 +18,22 @@ struct LinearParams {
     float *C = nullptr; int ldc = 0;
     float *Dv = nullptr; int lddv = 0;                       // SOFTPLUS: derivative of the activation (optional)
     const float *Mul = nullptr; int ldmul = 0; long long mul_div = 1;        // MULT: C = t * Mul[row / mul_div][n]
+    const float *row_scale = nullptr;                        // MULT: additional factor row_scale[row]
+    // batched launch (gridDim.z): entry z reads A1 + z sA1, Mul + z sMul, row_scale + z sRow, writes C + z sC (strides in floats)
+    // and uses weight set z/2 for z < 2 w_pairs, z - w_pairs beyond (the mirrored pairs of the ensemble share weights)
+    int batch = 1; long long sA1 = 0, sC = 0, sMul = 0, sRow = 0; int w_pairs = 0;
     // filled by launch_linear from the packed weights
-    const uint8_t *W = nullptr; int N = 0, Nt = 0, ksteps = 0;
+    const uint8_t *W = nullptr; long long w_stride = 0; int N = 0, Nt = 0, ksteps = 0, stages = 0;
 };
 
 struct PackedLinear {
     DeviceBuffer slabs;
-    int N = 0, K = 0, Nt = 0, n_tiles = 0, ksteps = 0;
-    // B[n][k] = scale * (transpose ? W[k_off + k][n_off + n] : W[n_off + n][k_off + k]),  n < N, k < K
-    int pack(const float *W_dev, int ldw, int N, int K, int n_off, int k_off, bool transpose, float scale, cudaStream_t stream);
+    int N = 0, K = 0, Nt = 0, n_tiles = 0, ksteps = 0, sets = 1;
+    size_t set_bytes = 0;
+    // B[n][k] = scale * k_scale[k] * (transpose ? W[k_off + k][n_off + n] : W[n_off + n][k_off + k]),  n < N, k < K;
+    // `sets` matrices W + s * w_set_stride (k_scale + s * k_scale_stride) packed back to back
+    int pack(const float *W_dev, int ldw, int N, int K, int n_off, int k_off, bool transpose, float scale, cudaStream_t stream,
+             int sets = 1, long long w_set_stride = 0, const float *k_scale_dev = nullptr, long long k_scale_stride = 0);
 };
 
 int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream);
