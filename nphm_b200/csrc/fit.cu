@@ -59,7 +59,7 @@ struct Buffers {
     float *member_s;                // n x members
     const unsigned char *mask;      // optional n: 0 = the point is excluded from the loss (joint fitter: failed correspondences)
     float *grad_points;             // optional n x 3: d loss / d point (accumulated over members with atomics)
-    float *acts;                    // optional: activation derivatives saved by the tensor-core forward, [member][rows][tc::kActLd];
+    float *acts;                    // optional: activation derivatives saved by the tensor-core forward, [member][tile][tc::kActLd][128];
                                     // the backward GEMMs overwrite them with the layer deltas
     float *out, *S, *gsign;         // n each
     float *acc;                     // members x 2H   (sum delta0 | sum delta2)
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) fit_member_kernel(const Dims d, c
 // ---------------------------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward pass of the tensor-core path, layer by layer on tcgen05 (tc_linear.cu, batched over the members):
-//   the forward (tc::ensemble_tc_kernel_v8<.., ACTS>) leaves sigma'_l = d softplus / d pre-activation of every hidden unit, one row
-//   of tc::kActLd floats per (member, point);
+//   the forward (tc::ensemble_tc_kernel_v8<.., ACTS>) leaves sigma'_l = d softplus / d pre-activation of every hidden unit, a block
+//   of tc::kActLd features x 128 points per (member, 128-point tile);
 //   fit_upstream_kernel   g_s[m][p] = dL/d s_m(p) (blend + loss), blend-weight gradients w.r.t. anchors and points
 //   3 batched GEMMs       delta2 = sigma'2 * (sigma'3 (diag(w4) W3));  delta1 = sigma'1 * (delta2 W2[:, :N1]) / sqrt2;
 //                         delta0 = sigma'0 * (delta1 W1)      - per unit upstream gradient (times kDeltaScale), each written in
@@ -284,84 +284,78 @@ __global__ void __launch_bounds__(256) fit_upstream_kernel(const Dims d, const B
         if (s_acc[i] != 0.f) atomicAdd(b.blend_acc + i, s_acc[i]);
 }
 
-// warp per (member, point) row of the delta blocks: column sums of delta0 / delta2 and (POINTS) the gradient w.r.t. the point
-// through the member's local coordinates.  grid (ceil(n / kReduceRows), members), kReduceRows rows per CTA.
-constexpr int kReduceRows = 128, kReduceWarps = 8;
+// one CTA per (128-point tile, member) block of deltas [feature][128]: g_s-weighted sums of delta0 / delta2 over the points
+// (-> acc) and (POINTS) the gradient w.r.t. every point through the member's local coordinates.  Lane = 4 points, the
+// warps split the features.
+constexpr int kReduceWarps = 8;
 constexpr float kDeltaScale = 64.0f;          // the GEMMs carry the deltas per unit upstream gradient, times this power of two: the
                                               // fp16 hi/lo operand split needs O(1) magnitudes (g_s itself is ~1e-4 / n_points)
 template <bool POINTS>
 __global__ void __launch_bounds__(32 * kReduceWarps) fit_reduce_kernel(const Dims d, const Weights w, const Buffers b,
-                                                                      const float *__restrict__ deltas, long long rows_per_member,
+                                                                      const float *__restrict__ deltas, long long tiles,
                                                                       const float *__restrict__ gs)
 {
-    constexpr int kCols = 7;                                  // columns per lane: lane + 32 i  (H <= 224)
-    __shared__ float s_sum[2 * 224];
+    __shared__ float s_g[kReduceWarps][3][128];
+    __shared__ float s_w[2][224][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.y;
     const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
-    const bool mirror = (m & 1) && m < 2 * d.n_symm;
-    for (int i = threadIdx.x; i < 2 * 224; i += blockDim.x) s_sum[i] = 0.f;
-    __syncthreads();
-    float w0[kCols][3], w2[kCols][3];
+    const long long row0 = (long long)blockIdx.x * 128;
     if (POINTS) {
         const int in0 = 3 + d.C;
         const float *W0 = w.W[0] + (size_t)set * d.H * in0;
         const float *W2 = w.W[2] + (size_t)set * d.H * d.H + d.N1;
-#pragma unroll
-        for (int i = 0; i < kCols; ++i) {
-            const int j = lane + 32 * i;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                w0[i][a] = j < d.H ? __ldg(W0 + (size_t)j * in0 + a) : 0.f;
-                w2[i][a] = j < d.H ? 0.70710678118654752f * __ldg(W2 + (size_t)j * d.H + a) : 0.f;
-            }
+        for (int i = threadIdx.x; i < d.H * 3; i += blockDim.x) {
+            const int j = i / 3, a = i % 3;
+            s_w[0][j][a] = __ldg(W0 + (size_t)j * in0 + a);
+            s_w[1][j][a] = 0.70710678118654752f * __ldg(W2 + (size_t)j * d.H + a);
         }
+        __syncthreads();
     }
-    float c0[kCols], c2[kCols];
+    // upstream gradient of s_m at this lane's 4 points (zero beyond the last point: the padding rows of the block hold garbage)
+    float up[4];
 #pragma unroll
-    for (int i = 0; i < kCols; ++i) { c0[i] = 0.f; c2[i] = 0.f; }
-    const long long r_begin = (long long)blockIdx.x * kReduceRows;
-    for (int rr = warp; rr < kReduceRows; rr += kReduceWarps) {
-        const long long row = r_begin + rr;
-        if (row >= b.n) break;
-        const float *src = deltas + ((size_t)m * rows_per_member + row) * tc::kActLd;
-        const float up = gs[(size_t)m * rows_per_member + row] * (1.0f / kDeltaScale);      // upstream gradient of s_m(row)
-        if (up == 0.f) continue;
-        float g[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < kCols; ++i) {
-            const int j = lane + 32 * i;
-            const float d0 = j < d.H ? up * src[tc::kActOff0 + j] : 0.f;
-            const float d2 = j < d.H ? up * src[tc::kActOff2 + j] : 0.f;
-            c0[i] += d0; c2[i] += d2;
-            if (POINTS) {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) g[a] = fmaf(w0[i][a], d0, fmaf(w2[i][a], d2, g[a]));
-            }
-        }
-        if (POINTS) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-#pragma unroll
-                for (int o = 16; o; o >>= 1) g[a] += __shfl_xor_sync(0xffffffffu, g[a], o);
-            }
-            if (mirror) g[0] = -g[0];
-            if (lane < 3) {
-                const float v = lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]);
-                if (v != 0.f) atomicAdd(b.grad_points + row * 3 + lane, v);
-            }
-        }
+    for (int i = 0; i < 4; ++i) {
+        const long long row = row0 + lane * 4 + i;
+        up[i] = row < b.n ? gs[(size_t)m * tiles * 128 + row] * (1.0f / kDeltaScale) : 0.f;
     }
-#pragma unroll
-    for (int i = 0; i < kCols; ++i) {
-        const int j = lane + 32 * i;
-        if (j < d.H) { atomicAdd(&s_sum[j], c0[i]); atomicAdd(&s_sum[224 + j], c2[i]); }
-    }
-    __syncthreads();
+    const float *blk = deltas + ((size_t)m * tiles + blockIdx.x) * tc::kActLd * 128;
     float *acc = b.acc + (size_t)m * 2 * d.H;
-    for (int i = threadIdx.x; i < 2 * d.H; i += blockDim.x) {
-        const float v = i < d.H ? s_sum[i] : s_sum[224 + i - d.H];
-        if (v != 0.f) atomicAdd(acc + i, v);
+    float g[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i][0] = g[i][1] = g[i][2] = 0.f;
+    for (int f = warp; f < 2 * d.H; f += kReduceWarps) {
+        const int which = f < d.H ? 0 : 1, j = which ? f - d.H : f;
+        const float4 v = *reinterpret_cast<const float4 *>(blk + (size_t)((which ? tc::kActOff2 : tc::kActOff0) + j) * 128 + lane * 4);
+        const float e[4] = {up[0] * v.x, up[1] * v.y, up[2] * v.z, up[3] * v.w};
+        float sum = (e[0] + e[1]) + (e[2] + e[3]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0 && sum != 0.f) atomicAdd(acc + f, sum);
+        if (POINTS) {
+            const float wx = s_w[which][j][0], wy = s_w[which][j][1], wz = s_w[which][j][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                g[i][0] = fmaf(wx, e[i], g[i][0]); g[i][1] = fmaf(wy, e[i], g[i][1]); g[i][2] = fmaf(wz, e[i], g[i][2]);
+            }
+        }
+    }
+    if (POINTS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) s_g[warp][a][lane * 4 + i] = g[i][a];
+        __syncthreads();
+        const bool mirror = (m & 1) && m < 2 * d.n_symm;
+        for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
+            const int pt = i / 3, a = i % 3;
+            float v = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kReduceWarps; ++ww) v += s_g[ww][a][pt];
+            if (a == 0 && mirror) v = -v;
+            const long long row = row0 + pt;
+            if (row < b.n && v != 0.f) atomicAdd(b.grad_points + row * 3 + a, v);
+        }
     }
 }
 
@@ -603,8 +597,7 @@ extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long 
     if (!h || n_points < 0) return -1;
     long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
                        (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
-    // activation derivatives handed from the tensor-core forward to the backward GEMMs ([member][rows][kActLd], rows padded to the
-    // 128-point tile) and the upstream gradient of every member output ([member][rows])
+    // activation derivatives handed from the tensor-core forward to the backward GEMMs ([member][tile][kActLd][128]) and the upstream gradient of every member output ([member][rows])
     floats += (long long)h->n_members * ((n_points + 127) / 128) * 128 * (nphm::tc::kActLd + 1);
     return floats * 4 + 1024;
 }
@@ -698,20 +691,21 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
         NPHM_CUDA_CHECK(cudaGetLastError());
         tcl::LinearParams lp{};
         lp.M = n_points; lp.mode = tcl::kModeMult; lp.batch = h->n_members; lp.w_pairs = d.n_symm;
+        lp.blocked = 1;                                   // [tile][feature][128 points] blocks, as the forward wrote them
         lp.lda1 = lp.ldmul = lp.ldc = tc::kActLd;
         lp.sA1 = lp.sMul = lp.sC = rows * tc::kActLd;
         // delta2 (over sigma'2): A = sigma'3
-        lp.A1 = acts + tc::kActOff3; lp.K1 = d.H; lp.Mul = acts + tc::kActOff2; lp.C = acts + tc::kActOff2;
+        lp.A1 = acts + tc::kActOff3 * 128; lp.K1 = d.H; lp.Mul = acts + tc::kActOff2 * 128; lp.C = acts + tc::kActOff2 * 128;
         if ((rc = tcl::launch_linear(bp.l3, lp, stream))) return rc;
         // delta1 (over sigma'1)
-        lp.A1 = acts + tc::kActOff2; lp.K1 = d.H; lp.Mul = acts + tc::kActOff1; lp.C = acts + tc::kActOff1;
+        lp.A1 = acts + tc::kActOff2 * 128; lp.K1 = d.H; lp.Mul = acts + tc::kActOff1 * 128; lp.C = acts + tc::kActOff1 * 128;
         if ((rc = tcl::launch_linear(bp.l2, lp, stream))) return rc;
         // delta0 (over sigma'0)
-        lp.A1 = acts + tc::kActOff1; lp.K1 = d.N1; lp.Mul = acts + tc::kActOff0; lp.C = acts + tc::kActOff0;
+        lp.A1 = acts + tc::kActOff1 * 128; lp.K1 = d.N1; lp.Mul = acts + tc::kActOff0 * 128; lp.C = acts + tc::kActOff0 * 128;
         if ((rc = tcl::launch_linear(bp.l1, lp, stream))) return rc;
-        dim3 rgrid((unsigned)ceil_div(n_points, fit::kReduceRows), h->n_members);
-        if (grad_points_dev) fit::fit_reduce_kernel<true><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows, gs);
-        else fit::fit_reduce_kernel<false><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows, gs);
+        dim3 rgrid((unsigned)(rows / 128), h->n_members);
+        if (grad_points_dev) fit::fit_reduce_kernel<true><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows / 128, gs);
+        else fit::fit_reduce_kernel<false><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows / 128, gs);
     } else {
         if (grad_points_dev) {
             set_error("gradient w.r.t. the points needs the tensor-core configuration (hidden 200, 4 layers, condition 96)");

@@ -305,7 +305,20 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
         p.blocked = 1;
     }
     p.n_tiles = n_tiles;
-    const int grid_x = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    p.member_groups = 1;
+    if (q.acts_out) {
+        // fitting: a few dozen tiles - split the members of a tile over several CTAs so that every SM has work.  Cost model:
+        // waves * (members per group + pipeline fill of a work item); groups must all be non-empty.
+        double best = 1e30;
+        for (int g = 1; g <= h->n_members; ++g) {
+            const int per = (h->n_members + g - 1) / g;
+            if (per * (g - 1) >= h->n_members) continue;
+            const double cost = (double)ceil_div(n_tiles * g, (long long)sm_count()) * (per + 0.7);
+            if (cost < best - 1e-9) { best = cost; p.member_groups = g; }
+        }
+    }
+    const long long n_items = n_tiles * p.member_groups;
+    const int grid_x = (int)(n_items < sm_count() ? n_items : sm_count());
     if ((rc = tc::launch_ensemble_v8(p, prune, q.acts_out != nullptr, grid_x, stream))) return rc;
     return NPHM_OK;
 }

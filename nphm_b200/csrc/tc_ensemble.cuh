@@ -58,11 +58,12 @@ struct Params {
     long long quirk_period;
     float *out;
     float *members_out;         // optional [n_queries][n_points][n_members]: un-blended member outputs s_k (fitting)
-    float *acts_out;            // optional [n_members][tiles * 128][kActLd]: activation derivatives (fitting backward)
+    float *acts_out;            // optional [n_members][tiles][kActLd][128]: activation derivatives (fitting backward)
     int n_members, n_symm;
     // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
     const float *anchors;       // [n_queries][n_members-1][3]
     float prune_tau;
+    int member_groups;          // activation-dump variant: CTAs per tile (each evaluates a range of members), >= 1
     long long n_tiles;          // tiles to process (grid mode + pruning uses compact 8x4x4 blocks)
     int blocked, px0, px1, by, bz;
 };

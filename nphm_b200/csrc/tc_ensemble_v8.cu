@@ -165,6 +165,17 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tiles_per_query = p.blocked ? p.n_tiles : (p.n_points + 127) / 128;
     const long long n_tiles = p.n_tiles;
+    // ACTS (fitting: few points, so few tiles): the members of a tile are split over `member_groups` CTAs - a work item is
+    // (tile, group of consecutive members), the in-kernel blend is meaningless then and `out` is not written
+    const int n_groups = ACTS ? p.member_groups : 1;
+    const long long n_items = n_tiles * n_groups;
+    auto group_mask = [&](long long item) -> unsigned long long {
+        const unsigned long long all = (1ull << p.n_members) - 1;
+        if (!ACTS || n_groups == 1) return all;
+        const int per = (p.n_members + n_groups - 1) / n_groups, lo = (int)(item % n_groups) * per;
+        const int hi = min(p.n_members, lo + per);
+        return ((1ull << hi) - 1) & ~((1ull << lo) - 1);
+    };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
@@ -193,9 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
         if (lane == 0) {
             int wb = 0;
             uint32_t wph = 0, tcount = 0, rcount = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+                const long long tile = ACTS ? item / n_groups : item;
                 const int qi = (int)(tile / tiles_per_query);
-                unsigned long long mask = (1ull << p.n_members) - 1;
+                unsigned long long mask = group_mask(item);
                 if (PRUNE) {
                     mbar_wait(&sm.mask_ready, tcount & 1);
                     const unsigned long long *mq = sm.maskq[tcount & 1];
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 };
                 load_rec(__ffsll((long long)mask) - 1);
                 for (int m = 0; m < p.n_members; ++m) {
-                    if (PRUNE && !((mask >> m) & 1)) continue;
+                    if ((PRUNE || ACTS) && !((mask >> m) & 1)) continue;
                     {
                         const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
                         if (rest) load_rec(m + 1 + (__ffsll((long long)rest) - 1));
@@ -261,15 +273,16 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 }
             };
             auto commit = [&](uint64_t *bar) { if (leader) tc_commit(bar); };
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                unsigned long long mask = (1ull << p.n_members) - 1;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+                const long long tile = ACTS ? item / n_groups : item;
+                unsigned long long mask = group_mask(item);
                 if (PRUNE) {
                     mbar_wait(&sm.mask_ready, tcount & 1);
                     const unsigned long long *mq = sm.maskq[tcount & 1];
                     mask = mq[0] | mq[1] | mq[2] | mq[3];
                 }
                 for (int m = 0; m < p.n_members; ++m) {
-                    if (PRUNE && !((mask >> m) & 1)) continue;
+                    if ((PRUNE || ACTS) && !((mask >> m) & 1)) continue;
                     auto next_buf = [&]() { if (++wb == 2) { wb = 0; wph ^= 1; } };
                     // ---- layer 1 (N 112): A0 units 0-5 from S (written one member ahead), 6-12 from P; D1 -> Q[0,112)
                     {
@@ -354,7 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
         uint32_t d_ph = 0, tcount = 0, rcount = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+                const long long tile = ACTS ? item / n_groups : item;
             int qi;
             long long idx, g;
             bool valid;
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             }
             const bool quirk = p.quirk_period > 0 && ((g % p.quirk_period) == p.quirk_period - 1 || g == p.total - 1);
             float num = 0.f, den = 0.f;
-            unsigned long long mask = (1ull << p.n_members) - 1;
+            unsigned long long mask = group_mask(item);
             if (PRUNE) {
                 // blend weights of all members for this thread's point: S = sum_k w_k; a member is needed by the tile if
                 // w_k >= tau * (S + 1e-6) for at least one of its points (dropped mass per point < n_members * tau).
@@ -428,22 +442,19 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             }
 
             // for the fitting backward: the derivative of every hidden activation, sigma'(pre) = 1 - 2^(-softplus) (v is the
-            // softplus in log2 units), one row of kActLd floats per (member, point) - the operand layout of the layer-wise
-            // backward GEMMs (fit.cu).  Columns beyond a layer's width receive don't-care values.
+            // softplus in log2 units).  Per (member, 128-point tile) a block of kActLd features x 128 points, feature-major - a
+            // warp store is one 128-byte line, and the layer-wise backward GEMMs (fit.cu, tc_linear.cu `blocked`) read it with
+            // thread = point.  Columns beyond a layer's width receive don't-care values.
             auto save_half = [&](float *ab, int col0, const float (&v)[8]) {
-                float s[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float ex;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-v[e]));
-                    s[e] = 1.0f - ex;
+                    ab[(size_t)(col0 + e) * 128 + row] = 1.0f - ex;
                 }
-                reinterpret_cast<float4 *>(ab + col0)[0] = make_float4(s[0], s[1], s[2], s[3]);
-                reinterpret_cast<float4 *>(ab + col0)[1] = make_float4(s[4], s[5], s[6], s[7]);
             };
             auto acts_of = [&](int member) -> float * {
-                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query * 128 + (size_t)(tile % tiles_per_query) * 128 + row) * kActLd
-                            : nullptr;
+                return ACTS ? p.acts_out + ((size_t)member * tiles_per_query + (tile % tiles_per_query)) * kActLd * 128 : nullptr;
             };
             auto publish = [&](uint64_t *bar) {          // my TMEM stores are visible to the MMA issuer after this
                 tc_wait_st();
@@ -680,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 acc_prev = layer3_dot(IC<kE3aUnits>(), IC<kUnits208 - kE3aUnits>(), IC<kOffE3b>(), rec_prev, ab_prev, acc_prev);
                 finalize(rec_prev, m_prev, rslot_prev, acc_prev);
             }
-            if (part == 0 && valid) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
+            if (part == 0 && valid && n_groups == 1) p.out[(size_t)qi * p.n_points + idx] = __fdiv_rn(num, den + 1e-6f);
         }
     }
 

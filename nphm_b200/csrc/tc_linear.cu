@@ -131,15 +131,20 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         const int t = threadIdx.x;                        // row of the tile = TMEM lane
         const long long row = row0 + t;
         const bool row_ok = row < p.M;
-        const float *a1 = p.A1 ? p.A1 + (size_t)z * p.sA1 + (size_t)(row_ok ? row : 0) * p.lda1 : nullptr;
+        // row-major: element (row, k) at row * lda + k.  blocked: tiles of 128 rows, feature-major inside a tile,
+        // (row, k) at (row / 128) * lda * 128 + k * 128 + row % 128 - what the fused ensemble forward writes (thread = point)
+        const size_t kstr = p.blocked ? 128 : 1;
+        const float *a1 = !p.A1 ? nullptr
+                          : p.blocked ? p.A1 + (size_t)z * p.sA1 + (size_t)blockIdx.x * p.lda1 * 128 + t
+                                      : p.A1 + (size_t)z * p.sA1 + (size_t)(row_ok ? row : 0) * p.lda1;
         const float *a2 = (p.A2 && !p.a2_onehot) ? p.A2 + (size_t)(row_ok ? row : 0) * p.lda2 : nullptr;
         const int hot = p.a2_onehot ? (int)(row % p.K2) : -1;
-        const bool vec_ok = p.A1 && (p.lda1 % 4 == 0) && (p.sA1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0);
+        const bool vec_ok = p.A1 && (p.blocked || ((p.lda1 % 4 == 0) && (p.sA1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0)));
         const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16;     // (row/8)*256 + (row%8)*16, + 128 for kk >= 8
         // the 16 inputs of k-step j: cols [16 j, 16 j + 16) of [A1 | A2], zero beyond the real width / the last row
         auto load_step = [&](int j, float (&v)[16]) {
             const int k0 = 16 * j;
-            if (row_ok && vec_ok && k0 + 16 <= p.K1) {
+            if (row_ok && vec_ok && !p.blocked && k0 + 16 <= p.K1) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 f = __ldg(reinterpret_cast<const float4 *>(a1 + k0) + i);
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                     const int k = k0 + c;
                     float x = 0.f;
                     if (row_ok) {
-                        if (k < p.K1) x = __ldg(a1 + k);
+                        if (k < p.K1) x = __ldg(a1 + (size_t)k * kstr);
                         else if (k < p.K1 + p.K2) x = p.a2_onehot ? (k - p.K1 == hot ? 1.f : 0.f) : __ldg(a2 + (k - p.K1));
                     }
                     v[c] = x;
@@ -165,10 +170,17 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         auto prefetch = [&](int j) {
             if (j < p.ksteps && fast(j)) {
                 const uint32_t dst = smem_u32(&a32[j % kARing][t][0]);
-                const float *src = a1 + 16 * j;
+                if (p.blocked) {
+                    const float *src = a1 + (size_t)(16 * j) * 128;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 4 * i) : "memory");
+                    for (int i = 0; i < 16; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * i), "l"(src + (size_t)i * 128) : "memory");
+                } else {
+                    const float *src = a1 + 16 * j;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 4 * i) : "memory");
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -206,7 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         tc_fence_after();
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
         const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
-        const float *mul = p.Mul ? p.Mul + (size_t)z * p.sMul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul : nullptr;
+        const float *mul = !p.Mul ? nullptr
+                           : p.blocked ? p.Mul + (size_t)z * p.sMul + (size_t)blockIdx.x * p.ldmul * 128 + t
+                                       : p.Mul + (size_t)z * p.sMul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul;
         const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
         float *const Cz = p.C + (size_t)z * p.sC;
         for (int c0 = 0; c0 < p.Nt; c0 += 16) {
@@ -219,7 +233,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
             {
                 const float *src = p.mode == kModeMult ? mul : bias;
                 const int lds = p.mode == kModeMult ? p.ldmul : p.ldb;
-                if (src && full && (lds % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                if (p.blocked) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? src[(size_t)(n0 + c0 + e) * 128] : 0.f;
+                } else if (src && full && (lds % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 f = reinterpret_cast<const float4 *>(src + n0 + c0)[i];      // plain loads: C may alias Mul
@@ -251,6 +268,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                     }
                 }
                 o[e] = x;
+            }
+            if (p.blocked) {
+                float *cb = Cz + (size_t)blockIdx.x * p.ldc * 128 + t;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (n0 + c0 + e < p.N) cb[(size_t)(n0 + c0 + e) * 128] = o[e];
+                continue;
             }
             float *crow = Cz + (size_t)row * p.ldc + n0 + c0;
             if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0)) {
@@ -343,6 +367,8 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
     NPHM_REQUIRE(w.slabs.ptr && p.C && p.M > 0, "tc_linear: unpacked weights or NULL output");
     NPHM_REQUIRE(p.K1 + p.K2 == w.K, "tc_linear: input width %d + %d does not match the packed weights (%d)", p.K1, p.K2, w.K);
     NPHM_REQUIRE(p.mode != kModeMult || (p.Mul && p.mul_div > 0), "tc_linear: multiplier missing");
+    NPHM_REQUIRE(!p.blocked || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot && p.mul_div <= 1),
+                 "tc_linear: the blocked layout supports the plain and the multiplier epilogue only");
     NPHM_REQUIRE(p.batch >= 1 && (p.batch == 1 || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot)),
                  "tc_linear: batched launches support the plain and the multiplier epilogue only");
     if (p.batch > 1) {

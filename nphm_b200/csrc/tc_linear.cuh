@@ -19,6 +19,8 @@ struct LinearParams {
     float *Dv = nullptr; int lddv = 0;                       // SOFTPLUS: derivative of the activation (optional)
     const float *Mul = nullptr; int ldmul = 0; long long mul_div = 1;        // MULT: C = t * Mul[row / mul_div][n]
     const float *row_scale = nullptr;                        // MULT: additional factor row_scale[row]
+    int blocked = 0;                                         // A1 / Mul / C in 128-row tiles, feature-major inside a tile:
+                                                             // (row, k) at (row / 128) * ld * 128 + k * 128 + row % 128
     // batched launch (gridDim.z): entry z reads A1 + z sA1, Mul + z sMul, row_scale + z sRow, writes C + z sC (strides in floats)
     // and uses weight set z/2 for z < 2 w_pairs, z - w_pairs beyond (the mirrored pairs of the ensemble share weights)
     int batch = 1; long long sA1 = 0, sC = 0, sMul = 0, sRow = 0; int w_pairs = 0;
