@@ -8,9 +8,11 @@
 //
 // Arithmetic: kind::f16 MMAs with fp32 accumulation in TMEM, both operands split x = hi + lo in two fp16 terms, products
 // hi*hi + hi*lo + lo*hi (3 MMAs per k-step) - the same fp32-level scheme as the fused kernels.  A is read as fp32 from
-// global memory and split on the fly by the four "row" warps (thread = row of the 128-row tile) into a 4-stage shared-memory
-// ring in UMMA K-major core-matrix order; W comes pre-split and pre-packed (pack_linear_kernel) through bulk async copies;
-// SS-form MMAs by one elected lane; the same four warps run the epilogue (thread = accumulator row).
+// global memory and split on the fly by eight "row" warps (thread = row of the 128-row tile x half of the k-step) into a 3- or
+// 4-stage shared-memory ring in UMMA K-major core-matrix order; W comes pre-split and pre-packed (pack_linear_kernel) through
+// bulk async copies; SS-form MMAs by one elected lane; the same eight warps run the epilogue (thread = accumulator row, every
+// other 16-column unit).  Operands are row-major or `blocked` ([128-row tile][feature][128]: what the fused ensemble forward
+// writes for the fitting backward); launches can be batched over gridDim.z with per-entry operands and weight sets.
 //
 //   A1 [M x K1] fp32 row-major, optional A2 [M x K2] appended along K (skip connection `cat([h, x])`, the 1/sqrt(2) is folded
 //   into W), or a one-hot A2 (row r -> e_{r mod K2}: the input tangents of a forward-mode pass, never materialised)
@@ -20,6 +22,7 @@
 //                    MULT     C = t * Mul[row / mul_div][n]                                         (tangent / adjoint passes)
 #include "tc_linear.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace nphm {
 namespace tcl {
@@ -27,7 +30,7 @@ using namespace tc;
 
 constexpr int kMaxStages = 4;                   // operand ring: 4 stages, 3 when two CTAs are to share an SM (batched launches)
 constexpr int kARing = 4;                       // fp32 staging ring of A (independent of the operand ring)
-constexpr int kRowWarps = 4;
+constexpr int kRowWarps = 8;                      // two per 32-row quarter of the tile
 constexpr int kThreads = 32 * (kRowWarps + 2);
 constexpr int kMaxNt = 256;
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
                  : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearParams p)
+__global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Ctl &sm = *reinterpret_cast<Ctl *>(smem_raw);
@@ -128,7 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         }
     } else {
         // ================================================================ row warps: split A into the ring, then the epilogue
-        const int t = threadIdx.x;                        // row of the tile = TMEM lane
+        // Two warps per 32-row quarter of the tile (TMEM lanes 32 (warp % 4) ..): `half` = warp / 4 converts inputs
+        // [8 half, 8 half + 8) of every k-step and finishes the accumulator units u with u % 2 == half.  (With one warp per
+        // quarter the kernel was bound by the dependent-instruction latency of 2 resident warps per scheduler.)
+        const int t = threadIdx.x & 127;                  // row of the tile = TMEM lane
+        const int half = warp >> 2, q = warp & 3;
         const long long row = row0 + t;
         const bool row_ok = row < p.M;
         // row-major: element (row, k) at row * lda + k.  blocked: tiles of 128 rows, feature-major inside a tile,
@@ -140,46 +147,37 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         const float *a2 = (p.A2 && !p.a2_onehot) ? p.A2 + (size_t)(row_ok ? row : 0) * p.lda2 : nullptr;
         const int hot = p.a2_onehot ? (int)(row % p.K2) : -1;
         const bool vec_ok = p.A1 && (p.blocked || ((p.lda1 % 4 == 0) && (p.sA1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A1) & 15) == 0)));
-        const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16;     // (row/8)*256 + (row%8)*16, + 128 for kk >= 8
-        // the 16 inputs of k-step j: cols [16 j, 16 j + 16) of [A1 | A2], zero beyond the real width / the last row
-        auto load_step = [&](int j, float (&v)[16]) {
-            const int k0 = 16 * j;
-            if (row_ok && vec_ok && !p.blocked && k0 + 16 <= p.K1) {
+        const uint32_t off0 = (uint32_t)(t >> 3) * 256 + (uint32_t)(t & 7) * 16 + (uint32_t)half * 128;   // core-matrix slot of (row, 8 half)
+        // this thread's 8 inputs of k-step j: cols [16 j + 8 half, + 8) of [A1 | A2], zero beyond the real width / the last row
+        auto load_direct = [&](int j, float (&v)[8]) {
+            const int k0 = 16 * j + 8 * half;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 f = __ldg(reinterpret_cast<const float4 *>(a1 + k0) + i);
-                    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+            for (int c = 0; c < 8; ++c) {
+                const int k = k0 + c;
+                float x = 0.f;
+                if (row_ok) {
+                    if (k < p.K1) x = __ldg(a1 + (size_t)k * kstr);
+                    else if (k < p.K1 + p.K2) x = p.a2_onehot ? (k - p.K1 == hot ? 1.f : 0.f) : __ldg(a2 + (k - p.K1));
                 }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int k = k0 + c;
-                    float x = 0.f;
-                    if (row_ok) {
-                        if (k < p.K1) x = __ldg(a1 + (size_t)k * kstr);
-                        else if (k < p.K1 + p.K2) x = p.a2_onehot ? (k - p.K1 == hot ? 1.f : 0.f) : __ldg(a2 + (k - p.K1));
-                    }
-                    v[c] = x;
-                }
+                v[c] = x;
             }
         };
-        // k-steps that lie inside A1 and are 16-byte aligned are staged through shared memory with cp.async, kADepth k-steps ahead
-        // (a thread only ever reads the row it copied itself, so cp.async.wait_group is all the synchronisation needed); the few
+        // inputs that lie inside A1 (and are 16-byte aligned) are staged through shared memory with cp.async, kADepth k-steps ahead
+        // (a thread only ever reads what it copied itself, so cp.async.wait_group is all the synchronisation needed); the few
         // others (skip-connection tail, one-hot tangents, K padding) are loaded directly
-        auto fast = [&](int j) { return row_ok && vec_ok && 16 * j + 16 <= p.K1; };
+        auto fast = [&](int j) { return row_ok && vec_ok && 16 * j + 8 * half + 8 <= p.K1; };
         auto prefetch = [&](int j) {
             if (j < p.ksteps && fast(j)) {
-                const uint32_t dst = smem_u32(&a32[j % kARing][t][0]);
+                const uint32_t dst = smem_u32(&a32[j % kARing][t][8 * half]);
                 if (p.blocked) {
-                    const float *src = a1 + (size_t)(16 * j) * 128;
+                    const float *src = a1 + (size_t)(16 * j + 8 * half) * 128;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
+                    for (int i = 0; i < 8; ++i)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * i), "l"(src + (size_t)i * 128) : "memory");
                 } else {
-                    const float *src = a1 + 16 * j;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 4 * i) : "memory");
+                    const float *src = a1 + 16 * j + 8 * half;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -187,72 +185,72 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
         for (int d = 0; d < kADepth; ++d) prefetch(d);
         for (int j = 0; j < p.ksteps; ++j) {
             const int s = j % kStages, sa = j % kARing;
-            float cur[16];
+            float cur[8];
             asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
             if (fast(j)) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 f = *reinterpret_cast<const float4 *>(&a32[sa][t][4 * i]);
-                    cur[4 * i] = f.x; cur[4 * i + 1] = f.y; cur[4 * i + 2] = f.z; cur[4 * i + 3] = f.w;
-                }
+                const float4 f0 = *reinterpret_cast<const float4 *>(&a32[sa][t][8 * half]);
+                const float4 f1 = *reinterpret_cast<const float4 *>(&a32[sa][t][8 * half + 4]);
+                cur[0] = f0.x; cur[1] = f0.y; cur[2] = f0.z; cur[3] = f0.w; cur[4] = f1.x; cur[5] = f1.y; cur[6] = f1.z; cur[7] = f1.w;
             } else {
-                load_step(j, cur);
+                load_direct(j, cur);
             }
             prefetch(j + kADepth);                             // slot (j + 3) % 4 was read by this thread at iteration j - 1
-            uint32_t hi[8], lo[8];
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
             mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
-            uint8_t *ah = st_a_hi(s) + off0, *al = st_a_lo(s) + off0;
-            *reinterpret_cast<uint4 *>(ah) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(ah + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<uint4 *>(al) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4 *>(al + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            *reinterpret_cast<uint4 *>(st_a_hi(s) + off0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(st_a_lo(s) + off0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a_full[s]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        // ---------------- epilogue: thread = row, 16 accumulator columns at a time
+        // ---------------- epilogue: thread = row, 16 accumulator columns at a time (units of this warp's parity)
         mbar_wait(&sm.d_ready, 0);
         tc_fence_after();
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
         const float *mul = !p.Mul ? nullptr
                            : p.blocked ? p.Mul + (size_t)z * p.sMul + (size_t)blockIdx.x * p.ldmul * 128 + t
                                        : p.Mul + (size_t)z * p.sMul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul;
         const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
         float *const Cz = p.C + (size_t)z * p.sC;
-        for (int c0 = 0; c0 < p.Nt; c0 += 16) {
+        const float *aux_src = p.mode == kModeMult ? mul : bias;      // bias (LINEAR / SOFTPLUS) or multiplier (MULT)
+        const int aux_ld = p.mode == kModeMult ? p.ldmul : p.ldb;
+        const bool aux_vec = aux_src && (aux_ld % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(aux_src) & 15) == 0);
+        const bool c_vec = (p.ldc % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+        const bool d_vec = p.Dv && (p.lddv % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Dv) & 15) == 0);
+        // FULL: all 16 columns of the unit exist (no per-column guards, constant address offsets)
+        auto finish_unit = [&](int c0, auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
             uint32_t r[16];
             tc_ld16(tl + c0, r);
-            tc_wait_ld();
-            if (!row_ok) continue;
-            float o[16], dv[16], aux[16];                      // aux: bias (LINEAR / SOFTPLUS) or multiplier (MULT) of the 16 columns
-            const bool full = n0 + c0 + 16 <= p.N;
-            {
-                const float *src = p.mode == kModeMult ? mul : bias;
-                const int lds = p.mode == kModeMult ? p.ldmul : p.ldb;
+            float aux[16];
+            if (row_ok) {
                 if (p.blocked) {
+                    const float *ab = aux_src ? aux_src + (size_t)(n0 + c0) * 128 : nullptr;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? src[(size_t)(n0 + c0 + e) * 128] : 0.f;
-                } else if (src && full && (lds % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    for (int e = 0; e < 16; ++e) aux[e] = (ab && (FULL || n0 + c0 + e < p.N)) ? ab[e * 128] : 0.f;
+                } else if (FULL && aux_vec) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 f = reinterpret_cast<const float4 *>(src + n0 + c0)[i];      // plain loads: C may alias Mul
+                        const float4 f = reinterpret_cast<const float4 *>(aux_src + n0 + c0)[i];      // plain loads: C may alias Mul
                         aux[4 * i] = f.x; aux[4 * i + 1] = f.y; aux[4 * i + 2] = f.z; aux[4 * i + 3] = f.w;
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) aux[e] = (src && n0 + c0 + e < p.N) ? src[n0 + c0 + e] : 0.f;
+                    for (int e = 0; e < 16; ++e) aux[e] = (aux_src && (FULL || n0 + c0 + e < p.N)) ? aux_src[n0 + c0 + e] : 0.f;
                 }
             }
+            tc_wait_ld();
+            if (!row_ok) return;
+            float o[16], dv[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const int n = n0 + c0 + e;
                 float x = __uint_as_float(r[e]);
                 dv[e] = 0.f;
-                if (n < p.N) {
+                if (FULL || n0 + c0 + e < p.N) {
                     if (p.mode == kModeMult) x *= aux[e] * rscale;
                     else {
                         x += aux[e];
@@ -270,34 +268,38 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const LinearPara
                 o[e] = x;
             }
             if (p.blocked) {
-                float *cb = Cz + (size_t)blockIdx.x * p.ldc * 128 + t;
+                float *cb = Cz + (size_t)blockIdx.x * p.ldc * 128 + (size_t)(n0 + c0) * 128 + t;
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    if (n0 + c0 + e < p.N) cb[(size_t)(n0 + c0 + e) * 128] = o[e];
-                continue;
+                    if (FULL || n0 + c0 + e < p.N) cb[e * 128] = o[e];
+                return;
             }
             float *crow = Cz + (size_t)row * p.ldc + n0 + c0;
-            if (full && (p.ldc % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0)) {
+            if (FULL && c_vec) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     reinterpret_cast<float4 *>(crow)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    if (n0 + c0 + e < p.N) crow[e] = o[e];
+                    if (FULL || n0 + c0 + e < p.N) crow[e] = o[e];
             }
             if (p.Dv) {
                 float *drow = p.Dv + (size_t)row * p.lddv + n0 + c0;
-                if (full && (p.lddv % 4 == 0) && (((n0 + c0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Dv) & 15) == 0)) {
+                if (FULL && d_vec) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         reinterpret_cast<float4 *>(drow)[i] = make_float4(dv[4 * i], dv[4 * i + 1], dv[4 * i + 2], dv[4 * i + 3]);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (n0 + c0 + e < p.N) drow[e] = dv[e];
+                        if (FULL || n0 + c0 + e < p.N) drow[e] = dv[e];
                 }
             }
+        };
+        for (int c0 = 16 * half; c0 < p.Nt; c0 += 32) {
+            if (n0 + c0 + 16 <= p.N) finish_unit(c0, std::true_type());
+            else finish_unit(c0, std::false_type());
         }
     }
 
