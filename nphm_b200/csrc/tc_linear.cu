@@ -47,6 +47,15 @@ constexpr int kA32Bytes = kARing * 128 * kAPitch * 4;
 __host__ __device__ inline int stage_bytes(int Nt) { return 2 * 128 * 32 + Nt * 64; }
 inline int smem_bytes(int Nt, int stages) { return kCtlBytes + stages * stage_bytes(Nt) + kA32Bytes; }
 
+#ifdef NPHM_TCL_TRACE
+// timeline of CTA (0,0,0): [role field][k-step] clock64 stamps (tools/tcl_trace.py)
+__device__ long long g_tcl_trace[16 * 64];
+#define TCL_EVT(cond, field, j) do { if ((cond) && p.Nt == 256 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) \
+    g_tcl_trace[(field) * 64 + (j)] = clock64(); } while (0)
+#else
+#define TCL_EVT(cond, field, j) do { } while (0)
+#endif
+
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -80,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     const int n0 = nt_idx * p.Nt;
     const uint32_t tmem_cols = p.Nt <= 32 ? 32 : (p.Nt <= 64 ? 64 : (p.Nt <= 128 ? 128 : 256));
 
+    TCL_EVT(threadIdx.x == 0, 10, 0);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sm.a_full[i], kRowWarps); mbar_init(&sm.b_full[i], 1); mbar_init(&sm.empty[i], 1); }
         mbar_init(&sm.d_ready, 1);
@@ -95,27 +105,31 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
     const int slab_bytes = p.Nt * 64;
+    TCL_EVT(threadIdx.x == 0, 10, 1);
 
     if (warp == kRowWarps) {
         // ================================================================ producer: weight slabs (bulk async copies)
         if (lane == 0) {
             const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
-            for (int j = 0; j < p.ksteps; ++j) {
-                const int s = j % kStages;
-                mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
+            for (int j = 0, s = 0, ph = 0; j < p.ksteps; ++j) {          // (stage, phase) counted, not divided: kStages is a runtime value
+                mbar_wait(&sm.empty[s], ph ^ 1);
+                TCL_EVT(true, 0, j);
                 mbar_expect_tx(&sm.b_full[s], slab_bytes);
                 bulk_g2s(st_b(s), w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == kRowWarps + 1) {
         // ================================================================ MMA issuer (whole warp runs the loop, one lane issues)
         const bool leader = elect_one();
         const uint32_t idesc = make_idesc_m(128, p.Nt);
-        for (int j = 0; j < p.ksteps; ++j) {
-            const int s = j % kStages;
-            const uint32_t ph = (j / kStages) & 1;
+        uint32_t ph = 0;
+        for (int j = 0, s = 0; j < p.ksteps; ++j) {
+            TCL_EVT(leader, 1, j);
             mbar_wait(&sm.a_full[s], ph);
+            TCL_EVT(leader, 2, j);
             mbar_wait(&sm.b_full[s], ph);
+            TCL_EVT(leader, 3, j);
             tc_fence_after();
             if (leader) {
                 const uint64_t a_hi = make_desc(smem_u32(st_a_hi(s)), 128, 256), a_lo = make_desc(smem_u32(st_a_lo(s)), 128, 256);
@@ -128,6 +142,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 if (j == p.ksteps - 1) tc_commit(&sm.d_ready);
             }
             __syncwarp();
+            if (++s == kStages) { s = 0; ph ^= 1; }
         }
     } else {
         // ================================================================ row warps: split A into the ring, then the epilogue
@@ -183,10 +198,12 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         for (int d = 0; d < kADepth; ++d) prefetch(d);
-        for (int j = 0; j < p.ksteps; ++j) {
-            const int s = j % kStages, sa = j % kARing;
+        for (int j = 0, s = 0, ph = 0; j < p.ksteps; ++j) {
+            const int sa = j % kARing;
             float cur[8];
+            TCL_EVT(threadIdx.x == 0, 4, j);
             asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
+            TCL_EVT(threadIdx.x == 0, 5, j);
             if (fast(j)) {
                 const float4 f0 = *reinterpret_cast<const float4 *>(&a32[sa][t][8 * half]);
                 const float4 f1 = *reinterpret_cast<const float4 *>(&a32[sa][t][8 * half + 4]);
@@ -198,17 +215,23 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split2(cur[2 * i], cur[2 * i + 1], hi[i], lo[i]);
-            mbar_wait(&sm.empty[s], ((j / kStages) & 1) ^ 1);
+            TCL_EVT(threadIdx.x == 0, 6, j);
+            mbar_wait(&sm.empty[s], ph ^ 1);
+            TCL_EVT(threadIdx.x == 0, 7, j);
             *reinterpret_cast<uint4 *>(st_a_hi(s) + off0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(st_a_lo(s) + off0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a_full[s]);
+            TCL_EVT(threadIdx.x == 0, 8, j);
+            if (++s == kStages) { s = 0; ph ^= 1; }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         // ---------------- epilogue: thread = row, 16 accumulator columns at a time (units of this warp's parity)
+        TCL_EVT(threadIdx.x == 0, 9, 0);
         mbar_wait(&sm.d_ready, 0);
         tc_fence_after();
+        TCL_EVT(threadIdx.x == 0, 9, 1);
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
         const float *mul = !p.Mul ? nullptr
@@ -301,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             if (n0 + c0 + 16 <= p.N) finish_unit(c0, std::true_type());
             else finish_unit(c0, std::false_type());
         }
+        TCL_EVT(threadIdx.x == 0, 9, 2);
     }
 
     tc_fence_before();
@@ -396,3 +420,13 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
 
 }  // namespace tcl
 }  // namespace nphm
+
+#ifdef NPHM_TCL_TRACE
+extern "C" int nphm_debug_tcl_trace(long long *host, int n_ll)
+{
+    using namespace nphm;
+    NPHM_CUDA_CHECK(cudaDeviceSynchronize());
+    NPHM_CUDA_CHECK(cudaMemcpyFromSymbol(host, tcl::g_tcl_trace, (size_t)n_ll * 8));
+    return NPHM_OK;
+}
+#endif
