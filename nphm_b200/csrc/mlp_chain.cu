@@ -10,7 +10,9 @@
 // network in the joint fitter.  The condition is constant over the points of a query, so its part of layers 0 and `skip` is
 // folded into per-query constants (simt.cu: cvec) and its gradient only needs the per-query column sums of d_0 and d_skip.
 #include "tc_linear.cuh"
+#include <algorithm>
 #include <cmath>
+#include <cuda_fp16.h>
 
 namespace nphm {
 namespace chain {
@@ -28,6 +30,54 @@ __global__ void column_sums_kernel(const float *__restrict__ X, int ld, long lon
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += X[((size_t)q * rows_per_query + r) * ld + c];
     if (r1 > r0) atomicAdd(out + (size_t)q * n_cols + c, s);
+}
+
+// The same sums over a PACKED activation buffer (tc_linear.cuh: per 128-row tile and k-step [128 x 16 fp16 hi | 128 x 16 fp16 lo],
+// core-matrix order; value = hi + lo).  grid (tiles, k-steps), 256 threads: thread = (row of the tile, 8 of the 16 columns).
+__global__ void __launch_bounds__(256) column_sums_packed_kernel(const uint8_t *__restrict__ X, int ksteps, long long M,
+                                                                 long long rows_per_query, int n_cols, float *__restrict__ out)
+{
+    __shared__ float s_sum[16];
+    const int r = threadIdx.x >> 1, ch = threadIdx.x & 1, lane = threadIdx.x & 31;
+    const int j = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * 128, row = row0 + r;
+    const bool ok = row < M;
+    const long long q = (ok ? row : M - 1) / rows_per_query;
+    const long long q_first = row0 / rows_per_query, q_last = (min(row0 + 127, M - 1)) / rows_per_query;
+    const bool block_uniform = q_first == q_last;
+    if (threadIdx.x < 16) s_sum[threadIdx.x] = 0.f;
+    __syncthreads();
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (ok) {
+        const uint8_t *src = X + ((size_t)blockIdx.x * ksteps + j) * 8192 + (size_t)(r >> 3) * 256 + (size_t)ch * 128 + (size_t)(r & 7) * 16;
+        const uint4 h = *reinterpret_cast<const uint4 *>(src), l = *reinterpret_cast<const uint4 *>(src + 4096);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&hw[i]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&lw[i]));
+            v[2 * i] = a.x + b.x; v[2 * i + 1] = a.y + b.y;
+        }
+    }
+    const int c0 = j * 16 + ch * 8;
+    if (block_uniform) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = v[i];
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane < 2 && x != 0.f) atomicAdd(&s_sum[ch * 8 + i], x);
+        }
+        __syncthreads();
+        if (threadIdx.x < 16 && j * 16 + threadIdx.x < n_cols && s_sum[threadIdx.x] != 0.f)
+            atomicAdd(out + (size_t)q_first * n_cols + j * 16 + threadIdx.x, s_sum[threadIdx.x]);
+    } else if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (c0 + i < n_cols && v[i] != 0.f) atomicAdd(out + (size_t)q * n_cols + c0 + i, v[i]);
+    }
 }
 
 // grad_cond[q][j] = sum_n W0[n][3 + j] * S0[q][n]  +  sum_n Ws[n][Nh + 3 + j] * Ss[q][n] / sqrt(2)
@@ -88,7 +138,9 @@ struct MlpChain {
     tcl::PackedLinear fwd[kMaxLayers];        // B = W_l restricted to its point-dependent columns (1/sqrt2 folded at the skip)
     tcl::PackedLinear adj[kMaxLayers];        // B = W_l^T (input-activation columns only)
     tcl::PackedLinear adj_x0, adj_xs;         // W_0[:, 0:3]^T and W_skip[:, Nh:Nh+3]^T / sqrt2  (gradient w.r.t. xyz)
-    DeviceBuffer H[kMaxLayers], S[kMaxLayers], T[2], D[2], sums0, sumss, out_tmp;
+    // activations between the layers live in the packed operand format (Hp: values, Tp: tangents, Dp: adjoints), the
+    // activation derivatives S in the blocked fp32 layout ([128-row tile][feature][128]) - every access of the passes is coalesced
+    DeviceBuffer Hp[kMaxLayers], S[kMaxLayers], Tp[2], Dp[2], Tlast, sums0, sumss, out_tmp, xtmp;
     int ld[kMaxLayers];
     long long value_rows = 0;                 // rows of the last value pass that kept the activation derivatives
     bool have_deriv = false;
@@ -108,7 +160,9 @@ int chain_pack(nphm_mlp *h, cudaStream_t stream)
         const int ldw = s.in_total[l];
         const float scale = l == s.skip ? chain::kInvSqrt2 : 1.0f;
         // forward: point-dependent leading columns (xyz | h_{l-1} | [h_{skip-1}, xyz])
-        if ((rc = c.fwd[l].pack(W, ldw, s.N[l], s.K[l], 0, 0, false, scale, stream))) return rc;
+        // (the layer in front of the skip layer reserves 3 output columns: its epilogue appends xyz / the tangent seeds)
+        if ((rc = c.fwd[l].pack(W, ldw, s.N[l], s.K[l], 0, 0, false, scale, stream, 1, 0, nullptr, 0, l + 1 == s.skip ? 3 : 0)))
+            return rc;
         // adjoint w.r.t. the input activations of layer l (l >= 1): columns [0, N_{l-1})
         if (l >= 1 && (rc = c.adj[l].pack(W, ldw, s.N[l - 1], s.N[l], 0, 0, true, scale, stream))) return rc;
         c.ld[l] = pad4(s.N[l]);
@@ -127,7 +181,10 @@ void chain_destroy(nphm_mlp *h)
     h->chain = nullptr;
 }
 
-// value pass over M = n_queries * n_points rows; keeps h_l and (want_deriv) s_l of every hidden layer; `out` = last layer
+static size_t packed_bytes(long long rows, int ksteps) { return (size_t)ceil_div(rows, 128) * ksteps * 8192; }
+
+// value pass over M = n_queries * n_points rows; keeps h_l (packed) and (want_deriv) s_l (blocked) of every hidden layer;
+// `out` = last layer, row-major
 static int value_pass(nphm_mlp *h, const float *xyz, int n_queries, long long n_points, bool want_deriv, float *out,
                       cudaStream_t stream)
 {
@@ -140,21 +197,20 @@ static int value_pass(nphm_mlp *h, const float *xyz, int n_queries, long long n_
         tcl::LinearParams p;
         p.M = M;
         if (l == 0) { p.A1 = xyz; p.lda1 = 3; p.K1 = 3; }
-        else {
-            p.A1 = c.H[l - 1].as<float>(); p.lda1 = c.ld[l - 1]; p.K1 = s.N[l - 1];
-            if (l == s.skip) { p.A2 = xyz; p.lda2 = 3; p.K2 = 3; }
-        }
+        else { p.Ap = c.Hp[l - 1].as<uint8_t>(); p.a_ksteps = c.fwd[l].ksteps; }     // at the skip layer: [h | xyz], appended below
         p.bias = h->cvec.as<float>() + s.coff[l]; p.ldb = s.cvec_stride; p.rows_per_bias = n_points;
         if (last) {
             p.mode = tcl::kModeLinear;
             p.C = out; p.ldc = s.N[l];
         } else {
-            if ((rc = c.H[l].reserve((size_t)M * c.ld[l] * sizeof(float)))) return rc;
+            const int ks = c.fwd[l].packed_ksteps_out();
+            if ((rc = c.Hp[l].reserve(packed_bytes(M, ks)))) return rc;
             p.mode = tcl::kModeSoftplus;
-            p.C = c.H[l].as<float>(); p.ldc = c.ld[l];
+            p.Cp = c.Hp[l].as<uint8_t>(); p.c_ksteps = ks;
+            if (l + 1 == s.skip) { p.app = xyz; p.app_ld = 3; p.app_w = 3; }
             if (want_deriv) {
-                if ((rc = c.S[l].reserve((size_t)M * c.ld[l] * sizeof(float)))) return rc;
-                p.Dv = c.S[l].as<float>(); p.lddv = c.ld[l];
+                if ((rc = c.S[l].reserve((size_t)ceil_div(M, 128) * 128 * c.ld[l] * sizeof(float)))) return rc;
+                p.Dv = c.S[l].as<float>(); p.lddv = c.ld[l]; p.dv_blocked = 1;
             }
         }
         if ((rc = tcl::launch_linear(c.fwd[l], p, stream))) return rc;
@@ -210,28 +266,32 @@ extern "C" int nphm_mlp_jacobian(nphm_mlp *h, const float *xyz_dev, const float 
         out = c.out_tmp.as<float>();
     }
     if ((rc = value_pass(h, xyz_dev, n_queries, n_points, true, out, stream))) return rc;
-    // tangent pass: rows (point, j), j = 0..2
-    int maxld = 4;
-    for (int l = 0; l < s.n_lin; ++l) maxld = c.ld[l] > maxld ? c.ld[l] : maxld;
+    // tangent pass: rows (point, j), j = 0..2; tangents between the layers packed, the last layer row-major for the layout kernel
+    int max_ks = 1;
+    for (int l = 0; l + 1 < s.n_lin; ++l) max_ks = std::max(max_ks, c.fwd[l].packed_ksteps_out());
     for (int i = 0; i < 2; ++i)
-        if ((rc = c.T[i].reserve((size_t)3 * M * maxld * sizeof(float)))) return rc;
+        if ((rc = c.Tp[i].reserve(packed_bytes(3 * M, max_ks)))) return rc;
+    const int ld_last = c.ld[s.n_lin - 1];
+    if ((rc = c.Tlast.reserve((size_t)3 * M * ld_last * sizeof(float)))) return rc;
     for (int l = 0; l < s.n_lin; ++l) {
         const bool last = l == s.n_lin - 1;
         tcl::LinearParams p;
         p.M = 3 * M;
         if (l == 0) { p.K1 = 0; p.K2 = 3; p.a2_onehot = 1; }
-        else {
-            p.A1 = c.T[(l - 1) & 1].as<float>(); p.lda1 = c.ld[l - 1]; p.K1 = s.N[l - 1];
-            if (l == s.skip) { p.K2 = 3; p.a2_onehot = 1; }
+        else { p.Ap = c.Tp[(l - 1) & 1].as<uint8_t>(); p.a_ksteps = c.fwd[l].ksteps; }
+        if (last) {
+            p.mode = tcl::kModeLinear;
+            p.C = c.Tlast.as<float>(); p.ldc = ld_last;
+        } else {
+            p.mode = tcl::kModeMult; p.Mul = c.S[l].as<float>(); p.ldmul = c.ld[l]; p.mul_div = 3; p.mul_blocked = 1;
+            p.Cp = c.Tp[l & 1].as<uint8_t>(); p.c_ksteps = c.fwd[l].packed_ksteps_out();
+            if (l + 1 == s.skip) { p.app_onehot = 1; p.app_w = 3; }               // d xyz / d xyz_j = e_j
         }
-        p.C = c.T[l & 1].as<float>(); p.ldc = c.ld[l];
-        if (last) p.mode = tcl::kModeLinear;
-        else { p.mode = tcl::kModeMult; p.Mul = c.S[l].as<float>(); p.ldmul = c.ld[l]; p.mul_div = 3; }
         if ((rc = tcl::launch_linear(c.fwd[l], p, stream))) return rc;
     }
     const long long total = M * out_dim * 3;
-    chain::jacobian_layout_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(c.T[(s.n_lin - 1) & 1].as<float>(),
-                                                                                      c.ld[s.n_lin - 1], M, out_dim, jac_dev);
+    chain::jacobian_layout_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(c.Tlast.as<float>(), ld_last, M, out_dim,
+                                                                                      jac_dev);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }
@@ -259,44 +319,50 @@ extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const
         // handle are reused (the joint fitter differentiates at the same points it just took the Jacobian at)
         NPHM_REQUIRE(c.value_rows == M && c.have_deriv, "nphm_mlp_backward_inputs: no matching value pass to reuse");
     }
-    int maxld = 4;
-    for (int l = 0; l < s.n_lin; ++l) maxld = c.ld[l] > maxld ? c.ld[l] : maxld;
+    int max_ks = 1;
+    for (int l = 1; l <= L; ++l) max_ks = std::max(max_ks, (s.N[l - 1] + 15) / 16);
     for (int i = 0; i < 2; ++i)
-        if ((rc = c.D[i].reserve((size_t)M * maxld * sizeof(float)))) return rc;
+        if ((rc = c.Dp[i].reserve(packed_bytes(M, max_ks)))) return rc;
     if ((rc = c.sums0.reserve((size_t)n_queries * s.N[0] * sizeof(float)))) return rc;
     if ((rc = c.sumss.reserve((size_t)n_queries * s.N[s.skip] * sizeof(float)))) return rc;
     NPHM_CUDA_CHECK(cudaMemsetAsync(c.sums0.ptr, 0, (size_t)n_queries * s.N[0] * sizeof(float), stream));
     NPHM_CUDA_CHECK(cudaMemsetAsync(c.sumss.ptr, 0, (size_t)n_queries * s.N[s.skip] * sizeof(float), stream));
-    auto col_sums = [&](const float *X, int ld, int n_cols, float *out) {
-        const int chunks = (int)(n_points >= 4096 ? 32 : (n_points >= 256 ? 8 : 1));
-        dim3 grid((unsigned)ceil_div(n_cols, 128), (unsigned)n_queries, (unsigned)chunks);
-        chain::column_sums_kernel<<<grid, 128, 0, stream>>>(X, ld, n_points, n_cols, out);
+    // the adjoint of a layer's pre-activations: row-major fp32 for the output layer (the caller's grad_out), packed below it
+    struct Adjoint { const float *rows; int ld; const uint8_t *packed; int ksteps; int width; };
+    auto as_input = [&](tcl::LinearParams &p, const Adjoint &d) {
+        if (d.packed) { p.Ap = d.packed; p.a_ksteps = d.ksteps; }
+        else { p.A1 = d.rows; p.lda1 = d.ld; p.K1 = d.width; }
     };
-    // d_{l-1} = s_{l-1} * (d_l W_l), from the output layer down to d_0;  d_l lives in D[l & 1]
-    const float *d_cur = grad_out_dev;
-    int ld_cur = out_dim;
+    auto col_sums = [&](const Adjoint &d, float *out) {
+        dim3 grid((unsigned)ceil_div(M, 128), (unsigned)d.ksteps);
+        chain::column_sums_packed_kernel<<<grid, 256, 0, stream>>>(d.packed, d.ksteps, M, n_points, d.width, out);
+    };
+    // d_{l-1} = s_{l-1} * (d_l W_l), from the output layer down to d_0;  d_l lives in Dp[l & 1]
+    Adjoint d_cur{grad_out_dev, out_dim, nullptr, 0, out_dim};
     for (int l = L; l >= 1; --l) {
         tcl::LinearParams p;
         p.M = M;
-        p.A1 = d_cur; p.lda1 = ld_cur; p.K1 = s.N[l];
-        p.mode = tcl::kModeMult; p.Mul = c.S[l - 1].as<float>(); p.ldmul = c.ld[l - 1]; p.mul_div = 1;
-        p.C = c.D[(l - 1) & 1].as<float>(); p.ldc = c.ld[l - 1];
+        as_input(p, d_cur);
+        p.mode = tcl::kModeMult; p.Mul = c.S[l - 1].as<float>(); p.ldmul = c.ld[l - 1]; p.mul_div = 1; p.mul_blocked = 1;
+        const int ks = (s.N[l - 1] + 15) / 16;
+        p.Cp = c.Dp[(l - 1) & 1].as<uint8_t>(); p.c_ksteps = ks;
         if ((rc = tcl::launch_linear(c.adj[l], p, stream))) return rc;
         if (l == s.skip) {
             // d_skip (the layer's pre-activation gradient) is d_cur here: its column sums feed the condition gradient
-            col_sums(d_cur, ld_cur, s.N[s.skip], c.sumss.as<float>());
+            NPHM_REQUIRE(d_cur.packed, "nphm_mlp_backward_inputs: skip layer directly below the output is not supported");
+            col_sums(d_cur, c.sumss.as<float>());
             NPHM_CUDA_CHECK(cudaGetLastError());
             if (grad_xyz_dev) {
                 tcl::LinearParams px;
-                px.M = M; px.A1 = d_cur; px.lda1 = ld_cur; px.K1 = s.N[s.skip];
+                px.M = M;
+                as_input(px, d_cur);
                 px.mode = tcl::kModeLinear; px.C = grad_xyz_dev; px.ldc = 3;
                 if ((rc = tcl::launch_linear(c.adj_xs, px, stream))) return rc;
             }
         }
-        d_cur = c.D[(l - 1) & 1].as<float>();
-        ld_cur = c.ld[l - 1];
+        d_cur = Adjoint{nullptr, 0, c.Dp[(l - 1) & 1].as<uint8_t>(), ks, s.N[l - 1]};
     }
-    col_sums(d_cur, ld_cur, s.N[0], c.sums0.as<float>());
+    col_sums(d_cur, c.sums0.as<float>());
     NPHM_CUDA_CHECK(cudaGetLastError());
     if (grad_cond_dev) {
         dim3 grid((unsigned)ceil_div(s.cond_dim, 128), (unsigned)n_queries);
@@ -308,12 +374,13 @@ extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const
     if (grad_xyz_dev) {
         // + d_0 W_0[:, 0:3]  (the skip-layer part was written above): through a temporary, then accumulate
         tcl::LinearParams px;
-        px.M = M; px.A1 = d_cur; px.lda1 = ld_cur; px.K1 = s.N[0];
+        px.M = M;
+        as_input(px, d_cur);
         px.mode = tcl::kModeLinear;
-        float *tmp = c.D[1].as<float>() == d_cur ? c.D[0].as<float>() : c.D[1].as<float>();
-        px.C = tmp; px.ldc = 4;
+        if ((rc = c.xtmp.reserve((size_t)M * 4 * sizeof(float)))) return rc;
+        px.C = c.xtmp.as<float>(); px.ldc = 4;
         if ((rc = tcl::launch_linear(c.adj_x0, px, stream))) return rc;
-        chain::add3_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(tmp, 4, M, grad_xyz_dev);
+        chain::add3_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(c.xtmp.as<float>(), 4, M, grad_xyz_dev);
         NPHM_CUDA_CHECK(cudaGetLastError());
     }
     return NPHM_OK;

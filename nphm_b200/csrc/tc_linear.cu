@@ -33,6 +33,7 @@ constexpr int kARing = 4;                       // fp32 staging ring of A (indep
 constexpr int kRowWarps = 8;                      // two per 32-row quarter of the tile
 constexpr int kThreads = 32 * (kRowWarps + 2);
 constexpr int kMaxNt = 256;
+constexpr int kPackedStep = 2 * 128 * 32;       // bytes of one k-step of a packed A tile: 128 x 16 fp16 hi | 128 x 16 fp16 lo
 
 constexpr int kAPitch = 20;                      // floats per staged fp32 row (16 + 4: 80-byte pitch spreads the banks)
 constexpr int kADepth = 3;                       // k-steps of A kept in flight per thread (cp.async groups)
@@ -111,11 +112,14 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
         // ================================================================ producer: weight slabs (bulk async copies)
         if (lane == 0) {
             const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
+            // packed A (operand-ready tiles written by the epilogue of the previous layer): one more bulk copy per k-step
+            const uint8_t *ap = p.Ap ? p.Ap + (size_t)z * p.sAp + (size_t)blockIdx.x * p.a_ksteps * kPackedStep : nullptr;
             for (int j = 0, s = 0, ph = 0; j < p.ksteps; ++j) {          // (stage, phase) counted, not divided: kStages is a runtime value
                 mbar_wait(&sm.empty[s], ph ^ 1);
                 TCL_EVT(true, 0, j);
-                mbar_expect_tx(&sm.b_full[s], slab_bytes);
+                mbar_expect_tx(&sm.b_full[s], slab_bytes + (ap ? kPackedStep : 0));
                 bulk_g2s(st_b(s), w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
+                if (ap) bulk_g2s(st_a_hi(s), ap + (size_t)j * kPackedStep, kPackedStep, &sm.b_full[s]);   // a_hi | a_lo are adjacent
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
         uint32_t ph = 0;
         for (int j = 0, s = 0; j < p.ksteps; ++j) {
             TCL_EVT(leader, 1, j);
-            mbar_wait(&sm.a_full[s], ph);
+            if (!p.Ap) mbar_wait(&sm.a_full[s], ph);
             TCL_EVT(leader, 2, j);
             mbar_wait(&sm.b_full[s], ph);
             TCL_EVT(leader, 3, j);
@@ -197,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        for (int d = 0; d < kADepth; ++d) prefetch(d);
-        for (int j = 0, s = 0, ph = 0; j < p.ksteps; ++j) {
+        if (!p.Ap) for (int d = 0; d < kADepth; ++d) prefetch(d);
+        for (int j = 0, s = 0, ph = 0; j < (p.Ap ? 0 : p.ksteps); ++j) {
             const int sa = j % kARing;
             float cur[8];
             TCL_EVT(threadIdx.x == 0, 4, j);
@@ -234,11 +238,18 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
         TCL_EVT(threadIdx.x == 0, 9, 1);
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float *bias = p.bias ? p.bias + (size_t)(row_ok ? row / p.rows_per_bias : 0) * p.ldb : nullptr;
+        const bool mul_blk = p.blocked || p.mul_blocked;
+        const long long mrow = row_ok ? row / p.mul_div : 0;                     // multiplier row (tangent passes: 3 rows per point)
         const float *mul = !p.Mul ? nullptr
-                           : p.blocked ? p.Mul + (size_t)z * p.sMul + (size_t)blockIdx.x * p.ldmul * 128 + t
-                                       : p.Mul + (size_t)z * p.sMul + (size_t)(row_ok ? row / p.mul_div : 0) * p.ldmul;
+                           : mul_blk ? p.Mul + (size_t)z * p.sMul + (size_t)(mrow >> 7) * p.ldmul * 128 + (mrow & 127)
+                                     : p.Mul + (size_t)z * p.sMul + (size_t)mrow * p.ldmul;
         const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
-        float *const Cz = p.C + (size_t)z * p.sC;
+        float *const Cz = p.C ? p.C + (size_t)z * p.sC : nullptr;
+        uint8_t *const cp = p.Cp ? p.Cp + (size_t)z * p.sCp + (size_t)blockIdx.x * p.c_ksteps * kPackedStep +
+                                       (size_t)(t >> 3) * 256 + (size_t)(t & 7) * 16 : nullptr;
+        const float *app = (p.app && row_ok) ? p.app + (size_t)row * p.app_ld : nullptr;       // appended input columns (skip connection)
+        const int app_hot = p.app_onehot ? (int)(row % p.app_w) : -1;
+        const bool aux_blk = p.mode == kModeMult ? mul_blk : false;
         const float *aux_src = p.mode == kModeMult ? mul : bias;      // bias (LINEAR / SOFTPLUS) or multiplier (MULT)
         const int aux_ld = p.mode == kModeMult ? p.ldmul : p.ldb;
         const bool aux_vec = aux_src && (aux_ld % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(aux_src) & 15) == 0);
@@ -251,11 +262,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             tc_ld16(tl + c0, r);
             float aux[16];
             if (row_ok) {
-                if (p.blocked) {
+                if (aux_blk) {
                     const float *ab = aux_src ? aux_src + (size_t)(n0 + c0) * 128 : nullptr;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) aux[e] = (ab && (FULL || n0 + c0 + e < p.N)) ? ab[e * 128] : 0.f;
-                } else if (FULL && aux_vec) {
+                } else if (FULL && aux_vec && !aux_blk) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 f = reinterpret_cast<const float4 *>(aux_src + n0 + c0)[i];      // plain loads: C may alias Mul
@@ -273,6 +284,12 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             for (int e = 0; e < 16; ++e) {
                 float x = __uint_as_float(r[e]);
                 dv[e] = 0.f;
+                if (!FULL && n0 + c0 + e >= p.N) {
+                    // beyond the layer's width: zero, or the columns appended for the next layer (`cat([h, xyz])`, tangent seeds)
+                    const int a = n0 + c0 + e - p.N;
+                    x = 0.f;
+                    if (a < p.app_w) x = p.app_onehot ? (a == app_hot ? 1.f : 0.f) : (app ? app[a] : 0.f);
+                }
                 if (FULL || n0 + c0 + e < p.N) {
                     if (p.mode == kModeMult) x *= aux[e] * rscale;
                     else {
@@ -290,6 +307,24 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 }
                 o[e] = x;
             }
+            if (cp && ((n0 + c0) >> 4) < p.c_ksteps) {
+                // operand-ready output: this unit is k-step (n0 + c0) / 16 of the next layer's A tile, fp16 hi | lo, core-matrix order
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+                uint8_t *dst = cp + (size_t)((n0 + c0) >> 4) * kPackedStep;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<uint4 *>(dst + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4 *>(dst + 4096 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+            if (p.Dv && (p.blocked || p.dv_blocked)) {
+                float *db = p.Dv + (size_t)blockIdx.x * p.lddv * 128 + (size_t)(n0 + c0) * 128 + t;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (FULL || n0 + c0 + e < p.N) db[e * 128] = dv[e];
+            }
+            if (!Cz) return;
             if (p.blocked) {
                 float *cb = Cz + (size_t)blockIdx.x * p.ldc * 128 + (size_t)(n0 + c0) * 128 + t;
 #pragma unroll
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 for (int e = 0; e < 16; ++e)
                     if (FULL || n0 + c0 + e < p.N) crow[e] = o[e];
             }
-            if (p.Dv) {
+            if (p.Dv && !p.dv_blocked) {
                 float *drow = p.Dv + (size_t)row * p.lddv + n0 + c0;
                 if (FULL && d_vec) {
 #pragma unroll
@@ -363,17 +398,18 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, int ldw, int N, 
 
 int choose_nt(int N)
 {
-    // widest tile <= 256 that keeps the padding small: N <= 256 -> one tile rounded up to 16; otherwise tiles of 256
-    if (N <= kMaxNt) return (N + 15) / 16 * 16;
-    return kMaxNt;
+    // as few tiles of <= 256 columns as possible, equally wide (277 -> 2 x 144, not 256 + 21), rounded up to 16
+    const int tiles = (N + kMaxNt - 1) / kMaxNt;
+    return ((N + tiles - 1) / tiles + 15) / 16 * 16;
 }
 
 int PackedLinear::pack(const float *W_dev, int ldw, int N_, int K_, int n_off, int k_off, bool transpose, float scale,
-                       cudaStream_t stream, int sets_, long long w_set_stride, const float *k_scale_dev, long long k_scale_stride)
+                       cudaStream_t stream, int sets_, long long w_set_stride, const float *k_scale_dev, long long k_scale_stride,
+                       int n_extra_)
 {
-    N = N_; K = K_;
-    Nt = choose_nt(N);
-    n_tiles = (N + Nt - 1) / Nt;
+    N = N_; K = K_; n_extra = n_extra_;
+    Nt = choose_nt(N + n_extra);
+    n_tiles = (N + n_extra + Nt - 1) / Nt;
     ksteps = (K + 15) / 16;
     sets = sets_ > 0 ? sets_ : 1;
     set_bytes = (size_t)n_tiles * ksteps * Nt * 64;
@@ -390,12 +426,20 @@ int PackedLinear::pack(const float *W_dev, int ldw, int N_, int K_, int n_off, i
 
 int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
 {
-    NPHM_REQUIRE(w.slabs.ptr && p.C && p.M > 0, "tc_linear: unpacked weights or NULL output");
-    NPHM_REQUIRE(p.K1 + p.K2 == w.K, "tc_linear: input width %d + %d does not match the packed weights (%d)", p.K1, p.K2, w.K);
+    NPHM_REQUIRE(w.slabs.ptr && (p.C || p.Cp) && p.M > 0, "tc_linear: unpacked weights or NULL output");
+    if (p.Ap) {
+        NPHM_REQUIRE(!p.A1 && !p.A2 && !p.a2_onehot && p.a_ksteps == w.ksteps,
+                     "tc_linear: packed input of %d k-steps does not match the packed weights (%d)", p.a_ksteps, w.ksteps);
+    } else {
+        NPHM_REQUIRE(p.K1 + p.K2 == w.K, "tc_linear: input width %d + %d does not match the packed weights (%d)", p.K1, p.K2, w.K);
+    }
+    NPHM_REQUIRE(!p.Cp || (p.c_ksteps >= (w.N + p.app_w + 15) / 16 && p.app_w <= w.n_extra && (!p.Dv || p.dv_blocked || p.C)),
+                 "tc_linear: packed output misconfigured");
+    NPHM_REQUIRE(p.app_w == 0 || p.Cp, "tc_linear: appended columns need a packed output");
     NPHM_REQUIRE(p.mode != kModeMult || (p.Mul && p.mul_div > 0), "tc_linear: multiplier missing");
-    NPHM_REQUIRE(!p.blocked || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot && p.mul_div <= 1),
+    NPHM_REQUIRE(!p.blocked || (!p.bias && !p.A2 && !p.a2_onehot && p.mul_div <= 1),
                  "tc_linear: the blocked layout supports the plain and the multiplier epilogue only");
-    NPHM_REQUIRE(p.batch >= 1 && (p.batch == 1 || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot)),
+    NPHM_REQUIRE(p.batch >= 1 && (p.batch == 1 || (!p.Dv && !p.bias && !p.A2 && !p.a2_onehot && !p.app)),
                  "tc_linear: batched launches support the plain and the multiplier epilogue only");
     if (p.batch > 1) {
         const int last = p.batch - 1, need = (last < 2 * p.w_pairs ? (last >> 1) : last - p.w_pairs) + 1;

@@ -19,6 +19,15 @@ struct LinearParams {
     float *Dv = nullptr; int lddv = 0;                       // SOFTPLUS: derivative of the activation (optional)
     const float *Mul = nullptr; int ldmul = 0; long long mul_div = 1;        // MULT: C = t * Mul[row / mul_div][n]
     const float *row_scale = nullptr;                        // MULT: additional factor row_scale[row]
+    int mul_blocked = 0, dv_blocked = 0;                     // Mul / Dv alone in the blocked layout (see `blocked`)
+    // operand-ready ("packed") activations: per 128-row tile and k-step 8 KB = [128 x 16 fp16 hi | 128 x 16 fp16 lo] in UMMA core-
+    // matrix order.  Cp: the epilogue writes its output split like that (unit u of 16 columns = k-step u of the next layer), so
+    // the next launch takes it as Ap with one bulk copy per k-step and no conversion work in its main loop.
+    const uint8_t *Ap = nullptr; int a_ksteps = 0; long long sAp = 0;        // replaces A1 / A2; 16 a_ksteps = packed K
+    uint8_t *Cp = nullptr; int c_ksteps = 0; long long sCp = 0;              // optional, in addition to / instead of C
+    // columns appended behind the layer's N outputs in Cp (the next layer's `cat([h, xyz])`): app[row][0..app_w) or, one-hot,
+    // e_{row mod app_w} (the tangent seeds of a forward-mode pass)
+    const float *app = nullptr; int app_ld = 0, app_w = 0, app_onehot = 0;
     int blocked = 0;                                         // A1 / Mul / C in 128-row tiles, feature-major inside a tile:
                                                              // (row, k) at (row / 128) * ld * 128 + k * 128 + row % 128
     // batched launch (gridDim.z): entry z reads A1 + z sA1, Mul + z sMul, row_scale + z sRow, writes C + z sC (strides in floats)
@@ -34,8 +43,12 @@ struct PackedLinear {
     size_t set_bytes = 0;
     // B[n][k] = scale * k_scale[k] * (transpose ? W[k_off + k][n_off + n] : W[n_off + n][k_off + k]),  n < N, k < K;
     // `sets` matrices W + s * w_set_stride (k_scale + s * k_scale_stride) packed back to back
+    // n_extra: output columns reserved behind N in the tiling (LinearParams::app)
     int pack(const float *W_dev, int ldw, int N, int K, int n_off, int k_off, bool transpose, float scale, cudaStream_t stream,
-             int sets = 1, long long w_set_stride = 0, const float *k_scale_dev = nullptr, long long k_scale_stride = 0);
+             int sets = 1, long long w_set_stride = 0, const float *k_scale_dev = nullptr, long long k_scale_stride = 0,
+             int n_extra = 0);
+    int packed_ksteps_out() const { return (N + n_extra + 15) / 16; }       // k-steps of the packed output (Cp) of this layer
+    int n_extra = 0;
 };
 
 int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream);
