@@ -72,6 +72,8 @@ struct nphm_mlp {
     nphm::DeviceBuffer tc_weights, tc_consts, tc_coff;
     bool tc_ready = false;
     const int *tc_live = nullptr;   // set around a launch by the Broyden loop: device counter, 0 = skip the evaluation
+    bool tc_records_fresh = false;  // set by the Broyden loop after its first evaluation: the per-query records of the tensor-core
+                                    // kernel are still those of this condition, do not rebuild them
     // layer-by-layer tensor-core passes: any width, Jacobian, adjoint (mlp_chain.cu)
     nphm::MlpChain *chain = nullptr;
 };

@@ -284,78 +284,93 @@ __global__ void __launch_bounds__(256) fit_upstream_kernel(const Dims d, const B
         if (s_acc[i] != 0.f) atomicAdd(b.blend_acc + i, s_acc[i]);
 }
 
-// one CTA per (128-point tile, member) block of deltas [feature][128]: g_s-weighted sums of delta0 / delta2 over the points
-// (-> acc) and (POINTS) the gradient w.r.t. every point through the member's local coordinates.  Lane = 4 points, the
-// warps split the features.
-constexpr int kReduceWarps = 8;
+// one CTA per (128-point tile, member): g_s-weighted sums of delta0 / delta2 over the points (-> acc) and (POINTS) the gradient
+// w.r.t. every point through the member's local coordinates.  The deltas come operand-ready from the GEMMs (packed: per k-step
+// of 16 features [128 x 16 fp16 hi | 128 x 16 fp16 lo], value = hi + lo); thread = (point, 8 of the 16 features of a k-step).
+constexpr int kReduceThreads = 256;
 constexpr float kDeltaScale = 64.0f;          // the GEMMs carry the deltas per unit upstream gradient, times this power of two: the
                                               // fp16 hi/lo operand split needs O(1) magnitudes (g_s itself is ~1e-4 / n_points)
+constexpr int kStepsH = 13, kStepsN1 = 7;     // packed k-steps of a hidden-width (200) / layer-1-width (101) block
+constexpr int kPackedPerTile = 2 * kStepsH + kStepsN1;      // [sigma'3 -> delta2 | delta1 | delta0]
 template <bool POINTS>
-__global__ void __launch_bounds__(32 * kReduceWarps) fit_reduce_kernel(const Dims d, const Weights w, const Buffers b,
-                                                                      const float *__restrict__ deltas, long long tiles,
-                                                                      const float *__restrict__ gs)
+__global__ void __launch_bounds__(kReduceThreads) fit_reduce_kernel(const Dims d, const Weights w, const Buffers b,
+                                                                   const uint8_t *__restrict__ packed, long long tiles,
+                                                                   const float *__restrict__ gs)
 {
-    __shared__ float s_g[kReduceWarps][3][128];
-    __shared__ float s_w[2][224][3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float s_sum[2][kStepsH * 16];
+    __shared__ float s_w[2][kStepsH * 16][3];
+    const int lane = threadIdx.x & 31;
+    const int r = threadIdx.x >> 1, ch = threadIdx.x & 1;
     const int m = blockIdx.y;
     const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
-    const long long row0 = (long long)blockIdx.x * 128;
+    const long long row = (long long)blockIdx.x * 128 + r;
+    for (int i = threadIdx.x; i < 2 * kStepsH * 16; i += blockDim.x) (&s_sum[0][0])[i] = 0.f;
     if (POINTS) {
         const int in0 = 3 + d.C;
         const float *W0 = w.W[0] + (size_t)set * d.H * in0;
         const float *W2 = w.W[2] + (size_t)set * d.H * d.H + d.N1;
-        for (int i = threadIdx.x; i < d.H * 3; i += blockDim.x) {
+        for (int i = threadIdx.x; i < kStepsH * 16 * 3; i += blockDim.x) {
             const int j = i / 3, a = i % 3;
-            s_w[0][j][a] = __ldg(W0 + (size_t)j * in0 + a);
-            s_w[1][j][a] = 0.70710678118654752f * __ldg(W2 + (size_t)j * d.H + a);
+            s_w[0][j][a] = j < d.H ? __ldg(W0 + (size_t)j * in0 + a) : 0.f;
+            s_w[1][j][a] = j < d.H ? 0.70710678118654752f * __ldg(W2 + (size_t)j * d.H + a) : 0.f;
         }
-        __syncthreads();
     }
-    // upstream gradient of s_m at this lane's 4 points (zero beyond the last point: the padding rows of the block hold garbage)
-    float up[4];
+    __syncthreads();
+    // upstream gradient of s_m at this thread's point (zero beyond the last point: the padding rows of a tile hold garbage)
+    const float up = row < b.n ? gs[(size_t)m * tiles * 128 + row] * (1.0f / kDeltaScale) : 0.f;
+    const uint8_t *tile = packed + ((size_t)m * tiles + blockIdx.x) * kPackedPerTile * 8192;
+    const size_t off = (size_t)(r >> 3) * 256 + (size_t)ch * 128 + (size_t)(r & 7) * 16;
+    float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+        const uint8_t *blk = tile + (size_t)(which ? 0 : kStepsH + kStepsN1) * 8192;       // delta2 first block, delta0 last
+        for (int j = 0; j < kStepsH; ++j) {
+            float v[8];
+            if (up != 0.f) {
+                const uint4 hq = *reinterpret_cast<const uint4 *>(blk + (size_t)j * 8192 + off);
+                const uint4 lq = *reinterpret_cast<const uint4 *>(blk + (size_t)j * 8192 + 4096 + off);
+                const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long row = row0 + lane * 4 + i;
-        up[i] = row < b.n ? gs[(size_t)m * tiles * 128 + row] * (1.0f / kDeltaScale) : 0.f;
-    }
-    const float *blk = deltas + ((size_t)m * tiles + blockIdx.x) * tc::kActLd * 128;
-    float *acc = b.acc + (size_t)m * 2 * d.H;
-    float g[4][3];
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&hw[i]));
+                    const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&lw[i]));
+                    v[2 * i] = up * (a.x + c.x); v[2 * i + 1] = up * (a.y + c.y);
+                }
+            } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) g[i][0] = g[i][1] = g[i][2] = 0.f;
-    for (int f = warp; f < 2 * d.H; f += kReduceWarps) {
-        const int which = f < d.H ? 0 : 1, j = which ? f - d.H : f;
-        const float4 v = *reinterpret_cast<const float4 *>(blk + (size_t)((which ? tc::kActOff2 : tc::kActOff0) + j) * 128 + lane * 4);
-        const float e[4] = {up[0] * v.x, up[1] * v.y, up[2] * v.z, up[3] * v.w};
-        float sum = (e[0] + e[1]) + (e[2] + e[3]);
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            }
+            const int f0 = j * 16 + ch * 8;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0 && sum != 0.f) atomicAdd(acc + f, sum);
-        if (POINTS) {
-            const float wx = s_w[which][j][0], wy = s_w[which][j][1], wz = s_w[which][j][2];
+            for (int i = 0; i < 8; ++i) {
+                float x = v[i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                g[i][0] = fmaf(wx, e[i], g[i][0]); g[i][1] = fmaf(wy, e[i], g[i][1]); g[i][2] = fmaf(wz, e[i], g[i][2]);
+                for (int o = 2; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane < 2 && x != 0.f) atomicAdd(&s_sum[which][f0 + i], x);
+                if (POINTS) {
+                    g[0] = fmaf(s_w[which][f0 + i][0], v[i], g[0]);
+                    g[1] = fmaf(s_w[which][f0 + i][1], v[i], g[1]);
+                    g[2] = fmaf(s_w[which][f0 + i][2], v[i], g[2]);
+                }
             }
         }
     }
     if (POINTS) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) s_g[warp][a][lane * 4 + i] = g[i][a];
-        __syncthreads();
+        for (int a = 0; a < 3; ++a) g[a] += __shfl_xor_sync(0xffffffffu, g[a], 1);
         const bool mirror = (m & 1) && m < 2 * d.n_symm;
-        for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
-            const int pt = i / 3, a = i % 3;
-            float v = 0.f;
+        if (mirror) g[0] = -g[0];
+        if (ch == 0 && row < b.n) {
 #pragma unroll
-            for (int ww = 0; ww < kReduceWarps; ++ww) v += s_g[ww][a][pt];
-            if (a == 0 && mirror) v = -v;
-            const long long row = row0 + pt;
-            if (row < b.n && v != 0.f) atomicAdd(b.grad_points + row * 3 + a, v);
+            for (int a = 0; a < 3; ++a)
+                if (g[a] != 0.f) atomicAdd(b.grad_points + row * 3 + a, g[a]);
         }
+    }
+    __syncthreads();
+    float *acc = b.acc + (size_t)m * 2 * d.H;
+    for (int i = threadIdx.x; i < 2 * d.H; i += blockDim.x) {
+        const float v = i < d.H ? s_sum[0][i] : s_sum[1][i - d.H];          // acc = [sum delta0 | sum delta2]
+        if (v != 0.f) atomicAdd(acc + i, v);
     }
 }
 
@@ -404,7 +419,9 @@ __global__ void fit_blend_kernel(const Dims d, const Buffers b, float clamp)
 }
 
 // per member: g_u = W0u^T D0 + W2u^T D2 / sqrt2 ; g_c = W0x^T D0 + W2x^T D2 / sqrt2
-__global__ void fit_member_grad_kernel(const Dims d, const Weights w, const Buffers b)
+// block = 128 columns x kGradSlices slices of the hidden index (partial sums through shared memory)
+constexpr int kGradSlices = 4;
+__global__ void __launch_bounds__(128 * kGradSlices) fit_member_grad_kernel(const Dims d, const Weights w, const Buffers b)
 {
     const int m = blockIdx.x;
     const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
@@ -414,22 +431,35 @@ __global__ void fit_member_grad_kernel(const Dims d, const Weights w, const Buff
     const float *W2 = w.W[2] + (size_t)set * d.H * in2;
     const float r2 = 0.70710678118654752f;
     __shared__ float gc[3];
-    for (int j = threadIdx.x; j < 3 + d.C; j += blockDim.x) {
+    __shared__ float part[kGradSlices][128];
+    const int col = threadIdx.x & 127, slice = threadIdx.x >> 7;
+    const int per = (d.H + kGradSlices - 1) / kGradSlices, n0 = slice * per, n1 = min(d.H, n0 + per);
+    for (int j0 = 0; j0 < 3 + d.C; j0 += 128) {
+        const int j = j0 + col;
         // j < 3: xyz columns; j >= 3: condition columns.  In W2 the order is [h1 (N1) | xyz (3) | cond (C)].
         float s0 = 0.f, s2 = 0.f;
-        for (int n = 0; n < d.H; ++n) {
-            s0 = fmaf(W0[(size_t)n * in0 + j], D0[n], s0);
-            s2 = fmaf(W2[(size_t)n * in2 + d.N1 + j], D2[n], s2);
+        if (j < 3 + d.C) {
+#pragma unroll 4
+            for (int n = n0; n < n1; ++n) {
+                s0 = fmaf(W0[(size_t)n * in0 + j], D0[n], s0);
+                s2 = fmaf(W2[(size_t)n * in2 + d.N1 + j], D2[n], s2);
+            }
         }
-        const float g = s0 + r2 * s2;
-        if (j < 3) gc[j] = g;
-        else {
-            const int u = j - 3;
-            if (u < d.G) atomicAdd(b.grad + u, g);
-            else b.grad[d.G + m * d.Lc + (u - d.G)] = g;
+        part[slice][col] = s0 + r2 * s2;
+        __syncthreads();
+        if (slice == 0 && j < 3 + d.C) {
+            float g = 0.f;
+#pragma unroll
+            for (int i = 0; i < kGradSlices; ++i) g += part[i][col];
+            if (j < 3) gc[j] = g;
+            else {
+                const int u = j - 3;
+                if (u < d.G) atomicAdd(b.grad + u, g);
+                else b.grad[d.G + m * d.Lc + (u - d.G)] = g;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < 3 && m < d.n_loc) {
         const bool mirror = (m & 1) && m < 2 * d.n_symm;
         // c = x - a (x component negated for mirrored members)  =>  d c / d a = -1 (+1 for the mirrored x)
@@ -445,7 +475,7 @@ struct FinalizeArgs {
 };
 
 // mlp_pos backward (anchor gradient -> z_glob), regularisers (fitting.py:252-268), loss terms, Adam
-__global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const Weights w, const Buffers b, float *latent,
+__global__ void __launch_bounds__(1024) fit_finalize_kernel(const Dims d, const Weights w, const Buffers b, float *latent,
                                                            float *adam_m, float *adam_v, const FinalizeArgs a,
                                                            float *loss_terms, float *grad_out)
 {
@@ -473,25 +503,32 @@ __global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const W
         }
         __syncthreads();
     }
-    // backward
-    for (int j = tid; j < Hd; j += nt) {
-        float s = 0.f;
-        for (int o = 0; o < O; ++o) s = fmaf(w.pos_w[2][(size_t)o * Hd + j], b.ganch[o], s);
-        g1[j] = h1[j] > 0.f ? s : 0.f;
-    }
-    __syncthreads();
-    for (int j = tid; j < Hd; j += nt) {
-        float s = 0.f;
-        for (int n = 0; n < Hd; ++n) s = fmaf(w.pos_w[1][(size_t)n * Hd + j], g1[n], s);
-        g0[j] = h0[j] > 0.f ? s : 0.f;
-    }
-    __syncthreads();
-    for (int j = tid; j < G; j += nt) {
-        float s = 0.f;
-        for (int n = 0; n < Hd; ++n) s = fmaf(w.pos_w[0][(size_t)n * G + j], g0[n], s);
-        b.grad[j] += s;
-    }
-    __syncthreads();
+    // backward: out[j] = sum_n W[n][j] v[n] for j < cols - threads (j, slice of n), partial sums through shared memory
+    float *scratch = red + 128;                                  // nt floats (red: 4 x 32 per-warp partials)
+    auto matvec_t = [&](const float *W, int ld, int rows, int cols, const float *v, auto &&store) {
+        const int cpad = cols <= 64 ? 64 : 256;                  // columns per pass (power of two <= nt)
+        const int slices = nt / cpad, slice = tid / cpad, jj = tid % cpad;
+        const int per = (rows + slices - 1) / slices, r0 = slice * per, r1 = min(rows, r0 + per);
+        for (int j0 = 0; j0 < cols; j0 += cpad) {
+            const int j = j0 + jj;
+            float s = 0.f;
+            if (j < cols) {
+#pragma unroll 4
+                for (int n = r0; n < r1; ++n) s = fmaf(W[(size_t)n * ld + j], v[n], s);
+            }
+            scratch[slice * cpad + jj] = s;
+            __syncthreads();
+            if (slice == 0 && j < cols) {
+                float t = 0.f;
+                for (int i = 0; i < slices; ++i) t += scratch[i * cpad + jj];
+                store(j, t);
+            }
+            __syncthreads();
+        }
+    };
+    matvec_t(w.pos_w[2], Hd, O, Hd, b.ganch, [&](int j, float t) { g1[j] = h1[j] > 0.f ? t : 0.f; });
+    matvec_t(w.pos_w[1], Hd, Hd, Hd, g1, [&](int j, float t) { g0[j] = h0[j] > 0.f ? t : 0.f; });
+    matvec_t(w.pos_w[0], G, Hd, G, g0, [&](int j, float t) { b.grad[j] += t; });
     // regularisers
     float part[4] = {0.f, 0.f, 0.f, 0.f};        // reg_global, reg_loc, reg_unobserved, (unused)
     const int unobs[3] = {30, 31, 39};
@@ -510,7 +547,7 @@ __global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const W
         float v = part[i];
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) red[i * 8 + (tid >> 5)] = v;
+        if ((tid & 31) == 0) red[i * 32 + (tid >> 5)] = v;
     }
     __syncthreads();
     // symmetric-pair distance: mean_i ||z_2i - z_2i+1||  (one warp per pair)
@@ -531,11 +568,11 @@ __global__ void __launch_bounds__(256) fit_finalize_kernel(const Dims d, const W
         }
         if ((tid & 31) == 0) symm_local += nrm;
     }
-    if ((tid & 31) == 0) red[24 + (tid >> 5)] = symm_local;
+    if ((tid & 31) == 0) red[96 + (tid >> 5)] = symm_local;
     __syncthreads();
     if (tid == 0 && loss_terms) {
         float rg = 0.f, rl = 0.f, ru = 0.f, sy = 0.f;
-        for (int wi = 0; wi < nt / 32; ++wi) { rg += red[wi]; rl += red[8 + wi]; ru += red[16 + wi]; sy += red[24 + wi]; }
+        for (int wi = 0; wi < nt / 32; ++wi) { rg += red[wi]; rl += red[32 + wi]; ru += red[64 + wi]; sy += red[96 + wi]; }
         loss_terms[0] = b.stats[1] / b.stats[0];      // surface = mean |sdf| over kept points (NaN if none, like torch)
         loss_terms[1] = rg; loss_terms[2] = rl; loss_terms[3] = ru;
         loss_terms[4] = d.n_symm ? sy / d.n_symm : 0.f;
@@ -597,9 +634,11 @@ extern "C" long long nphm_fit_workspace_bytes(const nphm_ensemble *h, long long 
     if (!h || n_points < 0) return -1;
     long long floats = n_points * (h->n_members + 3) + (long long)h->n_members * 2 * h->cfg.hidden_dim +
                        (long long)h->cfg.n_loc * 6 + 8 + h->lat_dim;
-    // activation derivatives handed from the tensor-core forward to the backward GEMMs ([member][tile][kActLd][128]) and the upstream gradient of every member output ([member][rows])
-    floats += (long long)h->n_members * ((n_points + 127) / 128) * 128 * (nphm::tc::kActLd + 1);
-    return floats * 4 + 1024;
+    // activation derivatives handed from the tensor-core forward to the backward GEMMs ([member][tile][kActLd][128], layers 0-2) and the upstream gradient of every member output ([member][rows])
+    const long long tiles = (n_points + 127) / 128;
+    floats += (long long)h->n_members * tiles * 128 * (nphm::tc::kActLd + 1);
+    // operand-ready (packed) sigma'3 / deltas of the backward GEMMs
+    return floats * 4 + (long long)h->n_members * tiles * nphm::fit::kPackedPerTile * 8192 + 1024;
 }
 
 static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_points, float *latent_dev,
@@ -674,6 +713,12 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
         q.cvec = h->cvec.as<float>(); q.anchors = h->anchors.as<float>(); q.blend = 1;
         q.out = b.out; q.members_out = b.member_s; q.exact = 1;
         q.acts_out = acts;
+        {
+            const long long rows = ceil_div(n_points, 128) * 128;
+            q.acts_packed_out = reinterpret_cast<unsigned char *>(acts + (size_t)h->n_members * rows * (tc::kActLd + 1));
+            // sigma'3 lands in the first kStepsH k-steps of every (member, tile) block of kPackedPerTile k-steps
+            q.acts_packed_tile_steps = fit::kPackedPerTile;
+        }
         if ((rc = tc_ensemble_launch(h, q, stream))) return rc;
         b.acts = acts;
     } else {
@@ -683,29 +728,34 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
     fit::fit_blend_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, stream>>>(d, b, fp->clamp);
     NPHM_CUDA_CHECK(cudaGetLastError());
     if (b.acts) {
-        const long long rows = ceil_div(n_points, 128) * 128;
+        const long long rows = ceil_div(n_points, 128) * 128, n_tiles = rows / 128;
         float *gs = acts + (size_t)h->n_members * rows * tc::kActLd;
+        uint8_t *packed = reinterpret_cast<uint8_t *>(gs + (size_t)h->n_members * rows);
         if ((rc = fit::backward_packs(h, stream))) return rc;
         const fit::BackwardPacks &bp = *h->fit_packs;
         fit::fit_upstream_kernel<<<(unsigned)ceil_div(n_points, 256), 256, 0, stream>>>(d, b, fp->lambda_surface, gs, rows);
         NPHM_CUDA_CHECK(cudaGetLastError());
+        // per (member, tile): packed [sigma'3 -> delta2 (13 k-steps) | delta1 (7) | delta0 (13)], blocked fp32 sigma'0 | sigma'1 | sigma'2
+        uint8_t *p32 = packed, *p1 = packed + (size_t)fit::kStepsH * 8192, *p0 = p1 + (size_t)fit::kStepsN1 * 8192;
         tcl::LinearParams lp{};
         lp.M = n_points; lp.mode = tcl::kModeMult; lp.batch = h->n_members; lp.w_pairs = d.n_symm;
-        lp.blocked = 1;                                   // [tile][feature][128 points] blocks, as the forward wrote them
-        lp.lda1 = lp.ldmul = lp.ldc = tc::kActLd;
-        lp.sA1 = lp.sMul = lp.sC = rows * tc::kActLd;
-        // delta2 (over sigma'2): A = sigma'3
-        lp.A1 = acts + tc::kActOff3 * 128; lp.K1 = d.H; lp.Mul = acts + tc::kActOff2 * 128; lp.C = acts + tc::kActOff2 * 128;
+        lp.mul_blocked = 1; lp.ldmul = tc::kActLd; lp.sMul = rows * tc::kActLd;
+        lp.sAp = lp.sCp = (long long)n_tiles * fit::kPackedPerTile * 8192;
+        // strides between the tiles of one member: tc_linear indexes packed tiles with a_ksteps / c_ksteps, so a tile pitch of
+        // kPackedPerTile k-steps is expressed through those counts
+        lp.a_tile_steps = lp.c_tile_steps = fit::kPackedPerTile;
+        // delta2 = sigma'2 * (sigma'3 (diag(w4) W3)), in place over sigma'3 (a CTA reads its tile before it writes it)
+        lp.Ap = p32; lp.a_ksteps = fit::kStepsH; lp.Mul = acts + tc::kActOff2 * 128; lp.Cp = p32; lp.c_ksteps = fit::kStepsH;
         if ((rc = tcl::launch_linear(bp.l3, lp, stream))) return rc;
-        // delta1 (over sigma'1)
-        lp.A1 = acts + tc::kActOff2 * 128; lp.K1 = d.H; lp.Mul = acts + tc::kActOff1 * 128; lp.C = acts + tc::kActOff1 * 128;
+        // delta1 = sigma'1 * (delta2 W2[:, :N1]) / sqrt2
+        lp.Ap = p32; lp.a_ksteps = fit::kStepsH; lp.Mul = acts + tc::kActOff1 * 128; lp.Cp = p1; lp.c_ksteps = fit::kStepsN1;
         if ((rc = tcl::launch_linear(bp.l2, lp, stream))) return rc;
-        // delta0 (over sigma'0)
-        lp.A1 = acts + tc::kActOff1 * 128; lp.K1 = d.N1; lp.Mul = acts + tc::kActOff0 * 128; lp.C = acts + tc::kActOff0 * 128;
+        // delta0 = sigma'0 * (delta1 W1)
+        lp.Ap = p1; lp.a_ksteps = fit::kStepsN1; lp.Mul = acts + tc::kActOff0 * 128; lp.Cp = p0; lp.c_ksteps = fit::kStepsH;
         if ((rc = tcl::launch_linear(bp.l1, lp, stream))) return rc;
-        dim3 rgrid((unsigned)(rows / 128), h->n_members);
-        if (grad_points_dev) fit::fit_reduce_kernel<true><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows / 128, gs);
-        else fit::fit_reduce_kernel<false><<<rgrid, 32 * fit::kReduceWarps, 0, stream>>>(d, w, b, acts, rows / 128, gs);
+        dim3 rgrid((unsigned)n_tiles, h->n_members);
+        if (grad_points_dev) fit::fit_reduce_kernel<true><<<rgrid, fit::kReduceThreads, 0, stream>>>(d, w, b, packed, n_tiles, gs);
+        else fit::fit_reduce_kernel<false><<<rgrid, fit::kReduceThreads, 0, stream>>>(d, w, b, packed, n_tiles, gs);
     } else {
         if (grad_points_dev) {
             set_error("gradient w.r.t. the points needs the tensor-core configuration (hidden 200, 4 layers, condition 96)");
@@ -714,7 +764,7 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
         fit::fit_member_kernel<true><<<grid, fit::kThreads, smem, stream>>>(d, w, b, fp->lambda_surface);
     }
     NPHM_CUDA_CHECK(cudaGetLastError());
-    fit::fit_member_grad_kernel<<<h->n_members, 128, 0, stream>>>(d, w, b);
+    fit::fit_member_grad_kernel<<<h->n_members, 128 * fit::kGradSlices, 0, stream>>>(d, w, b);
     NPHM_CUDA_CHECK(cudaGetLastError());
 
     fit::FinalizeArgs a{};
@@ -727,8 +777,8 @@ static int fit_step_impl(nphm_ensemble *h, const float *points_dev, long long n_
     a.bc2_sqrt = (float)std::sqrt(bc2);
     a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
     a.eps = 1e-8f; a.apply_update = apply_update;
-    const size_t fsm = (size_t)(4 * d.pos_hid + 64) * sizeof(float);
-    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
+    const size_t fsm = (size_t)(4 * d.pos_hid + 128 + 1024) * sizeof(float);
+    fit::fit_finalize_kernel<<<1, 1024, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }
@@ -846,8 +896,8 @@ extern "C" int nphm_fit_apply_gradient(nphm_ensemble *h, float *latent_dev, floa
     a.bc2_sqrt = (float)std::sqrt(bc2);
     a.one_minus_beta1 = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.one_minus_beta2 = (float)(1.0 - beta2);
     a.eps = 1e-8f; a.apply_update = apply_update;
-    const size_t fsm = (size_t)(4 * d.pos_hid + 64) * sizeof(float);
-    fit::fit_finalize_kernel<<<1, 256, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
+    const size_t fsm = (size_t)(4 * d.pos_hid + 128 + 1024) * sizeof(float);
+    fit::fit_finalize_kernel<<<1, 1024, fsm, stream>>>(d, w, b, latent_dev, adam_m_dev, adam_v_dev, a, loss_terms_dev, grad_out_dev);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }

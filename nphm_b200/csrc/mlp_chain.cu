@@ -85,17 +85,20 @@ __global__ void cond_grad_kernel(const float *__restrict__ W0, int ld0, int N0, 
                                  const float *__restrict__ Ws, int lds, int Ns, int skip_col0, const float *__restrict__ Ss,
                                  int cond_dim, float *__restrict__ out)
 {
+    // grid (column blocks, queries, chunks of the n range): `out` is zeroed by the caller, the chunks add their partial sums
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int q = blockIdx.y;
     if (j >= cond_dim) return;
+    const int c0 = (N0 + gridDim.z - 1) / gridDim.z, a0 = blockIdx.z * c0, b0 = min(N0, a0 + c0);
     float s = 0.f;
-    for (int n = 0; n < N0; ++n) s = fmaf(W0[(size_t)n * ld0 + 3 + j], S0[(size_t)q * N0 + n], s);
+    for (int n = a0; n < b0; ++n) s = fmaf(W0[(size_t)n * ld0 + 3 + j], S0[(size_t)q * N0 + n], s);
     if (Ws) {
+        const int c1 = (Ns + gridDim.z - 1) / gridDim.z, a1 = blockIdx.z * c1, b1 = min(Ns, a1 + c1);
         float t = 0.f;
-        for (int n = 0; n < Ns; ++n) t = fmaf(Ws[(size_t)n * lds + skip_col0 + j], Ss[(size_t)q * Ns + n], t);
+        for (int n = a1; n < b1; ++n) t = fmaf(Ws[(size_t)n * lds + skip_col0 + j], Ss[(size_t)q * Ns + n], t);
         s = fmaf(t, kInvSqrt2, s);
     }
-    out[(size_t)q * cond_dim + j] = s;
+    atomicAdd(out + (size_t)q * cond_dim + j, s);
 }
 
 // out[(q, n)][i][j] = T[(q, n, j)][i]   (tangent rows -> Jacobian layout B x N x out x 3)
@@ -147,6 +150,7 @@ struct MlpChain {
 };
 
 static int pad4(int n) { return (n + 3) / 4 * 4; }
+constexpr int kChainNt = 128;
 
 int chain_pack(nphm_mlp *h, cudaStream_t stream)
 {
@@ -161,10 +165,13 @@ int chain_pack(nphm_mlp *h, cudaStream_t stream)
         const float scale = l == s.skip ? chain::kInvSqrt2 : 1.0f;
         // forward: point-dependent leading columns (xyz | h_{l-1} | [h_{skip-1}, xyz])
         // (the layer in front of the skip layer reserves 3 output columns: its epilogue appends xyz / the tangent seeds)
-        if ((rc = c.fwd[l].pack(W, ldw, s.N[l], s.K[l], 0, 0, false, scale, stream, 1, 0, nullptr, 0, l + 1 == s.skip ? 3 : 0)))
+        // tiles of <= 128 output columns: the passes run on a few thousand rows (fitting), where CTAs count more than tile width
+        if ((rc = c.fwd[l].pack(W, ldw, s.N[l], s.K[l], 0, 0, false, scale, stream, 1, 0, nullptr, 0, l + 1 == s.skip ? 3 : 0,
+                                kChainNt)))
             return rc;
         // adjoint w.r.t. the input activations of layer l (l >= 1): columns [0, N_{l-1})
-        if (l >= 1 && (rc = c.adj[l].pack(W, ldw, s.N[l - 1], s.N[l], 0, 0, true, scale, stream))) return rc;
+        if (l >= 1 && (rc = c.adj[l].pack(W, ldw, s.N[l - 1], s.N[l], 0, 0, true, scale, stream, 1, 0, nullptr, 0, 0, kChainNt)))
+            return rc;
         c.ld[l] = pad4(s.N[l]);
     }
     if ((rc = c.adj_x0.pack(h->weights.W[0].as<float>(), s.in_total[0], 3, s.N[0], 0, 0, true, 1.0f, stream))) return rc;
@@ -365,7 +372,8 @@ extern "C" int nphm_mlp_backward_inputs(nphm_mlp *h, const float *xyz_dev, const
     col_sums(d_cur, c.sums0.as<float>());
     NPHM_CUDA_CHECK(cudaGetLastError());
     if (grad_cond_dev) {
-        dim3 grid((unsigned)ceil_div(s.cond_dim, 128), (unsigned)n_queries);
+        NPHM_CUDA_CHECK(cudaMemsetAsync(grad_cond_dev, 0, (size_t)n_queries * s.cond_dim * sizeof(float), stream));
+        dim3 grid((unsigned)ceil_div(s.cond_dim, 128), (unsigned)n_queries, 16);
         chain::cond_grad_kernel<<<grid, 128, 0, stream>>>(h->weights.W[0].as<float>(), s.in_total[0], s.N[0], c.sums0.as<float>(),
                                                           h->weights.W[s.skip].as<float>(), s.in_total[s.skip], s.N[s.skip],
                                                           s.N[s.skip - 1] + 3, c.sumss.as<float>(), s.cond_dim, grad_cond_dev);

@@ -182,6 +182,11 @@ __global__ void cvec_kernel(const PackSpec spec, const float *__restrict__ laten
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int l = 0; l < spec.n_layers; ++l) {
         const PackLayer &pl = spec.L[l];
+        if (!pl.folded) {                    // plain bias copy: thread per element
+            for (int n = blockIdx.z * blockDim.x + threadIdx.x; n < pl.Npad; n += gridDim.z * blockDim.x)
+                out[pl.coff + n] = n < pl.N ? pl.b[(size_t)set * pl.N + n] : 0.f;
+            continue;
+        }
         for (int n = blockIdx.z * wpb + warp; n < pl.Npad; n += gridDim.z * wpb) {
             float v = 0.f;
             if (n < pl.N) {

@@ -18,7 +18,9 @@ struct SimtQuery {
     int blend;                // 1: Gaussian anchor blend of member outputs (ensemble); 0: write channels
     float *out;
     float *members_out;       // optional (tensor-core kernel only): un-blended member outputs [q][point][member]
-    float *acts_out;          // optional (tensor-core kernel only): hidden activations, see tc::Params::acts_out
+    float *acts_out;          // optional (tensor-core kernel only): activation derivatives, see tc::Params::acts_out
+    unsigned char *acts_packed_out;   // goes with acts_out, see tc::Params::acts_packed_out
+    int acts_packed_tile_steps;
     int exact;                // 1: never use the opt-in pruned mode for this query (fitting needs every member)
 };
 

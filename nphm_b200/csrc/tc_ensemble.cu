@@ -288,10 +288,10 @@ int tc_ensemble_launch(nphm_ensemble *h, const SimtQuery &q, cudaStream_t stream
     p.l2_slabs = h->tc_l2slabs.as<uint8_t>();
     p.recs = h->tc_consts.as<float>();
     p.xyz = q.xyz; p.axes = q.axes; p.res = q.res; p.first = q.first; p.total = q.total; p.n_points = q.n_points;
-    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out; p.members_out = q.members_out; p.acts_out = q.acts_out;
+    p.n_queries = q.n_queries; p.quirk_period = q.quirk_period; p.out = q.out; p.members_out = q.members_out; p.acts_out = q.acts_out; p.acts_packed_out = q.acts_packed_out; p.acts_packed_tile_steps = q.acts_packed_tile_steps;
     p.n_members = h->n_members; p.n_symm = h->cfg.n_symm_pairs;
     const bool prune = h->tc_prune && !q.exact;
-    NPHM_REQUIRE(!q.acts_out || (q.n_queries == 1 && q.exact), "activation dump needs a single exact query");
+    NPHM_REQUIRE(!q.acts_out || (q.n_queries == 1 && q.exact && q.acts_packed_out && q.acts_packed_tile_steps >= tc::kActPackedSteps), "activation dump needs a single exact query");
     p.anchors = q.anchors; p.prune_tau = h->tc_prune_tau;
     p.blocked = 0; p.px0 = p.px1 = 0; p.by = p.bz = 1;
     long long n_tiles = ceil_div(q.n_points, 128) * q.n_queries;

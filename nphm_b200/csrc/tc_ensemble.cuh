@@ -33,7 +33,8 @@ constexpr int kColD2 = 304, kColA2Hi = 0, kColA2Lo = 104;
 constexpr int kColD3 = 208;
 constexpr int kRecSlots = 3;
 // activation derivatives saved per (member, point) for the fitting backward: sigma'0 [208] | sigma'1 [112] | sigma'2 [208] | sigma'3 [208]
-constexpr int kActOff0 = 0, kActOff1 = 208, kActOff2 = 320, kActOff3 = 528, kActLd = 736;
+constexpr int kActOff0 = 0, kActOff1 = 208, kActOff2 = 320, kActLd = 528;
+constexpr int kActPackedSteps = 13;               // sigma'3 goes out operand-ready: 13 k-steps of 8 KB per (member, tile)
 // per-(query, member) record, in floats
 constexpr int kRecL0 = 0;          // 208 x float4 (W0x row, S*v0), rows >= 200 are zero
 constexpr int kRecB1 = 832;        // 112
@@ -58,7 +59,9 @@ struct Params {
     long long quirk_period;
     float *out;
     float *members_out;         // optional [n_queries][n_points][n_members]: un-blended member outputs s_k (fitting)
-    float *acts_out;            // optional [n_members][tiles][kActLd][128]: activation derivatives (fitting backward)
+    float *acts_out;            // optional [n_members][tiles][kActLd][128]: activation derivatives of layers 0-2 (fitting backward)
+    uint8_t *acts_packed_out;   // with acts_out: [n_members][tiles][acts_packed_tile_steps >= kActPackedSteps][8 KB]: sigma'3 as
+    int acts_packed_tile_steps; // packed GEMM operand in the first kActPackedSteps k-steps of every (member, tile) block
     int n_members, n_symm;
     // pruned mode (opt-in): members whose normalised blend weight is < prune_tau for every point of a tile are skipped
     const float *anchors;       // [n_queries][n_members-1][3]

@@ -456,6 +456,23 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             auto acts_of = [&](int member) -> float * {
                 return ACTS ? p.acts_out + ((size_t)member * tiles_per_query + (tile % tiles_per_query)) * kActLd * 128 : nullptr;
             };
+            // sigma'3 is the A operand of the first backward GEMM: saved operand-ready (tc_linear.cuh "packed": per k-step = unit
+            // of 16 features [128 x 16 fp16 hi | 128 x 16 fp16 lo], core-matrix order), zeros in the K padding
+            auto save_packed3 = [&](const float *ab, int u, int h, const float (&v)[8], bool zero) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-v[2 * i]));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-v[2 * i + 1]));
+                    split2(zero ? 0.f : 1.0f - e0, zero ? 0.f : 1.0f - e1, hi[i], lo[i]);
+                }
+                const size_t blk = (size_t)(ab - p.acts_out) / ((size_t)kActLd * 128);
+                uint8_t *dst = p.acts_packed_out + (blk * p.acts_packed_tile_steps + u) * 8192 + (size_t)(row >> 3) * 256 + (size_t)h * 128 +
+                               (size_t)(row & 7) * 16;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(dst + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            };
             auto publish = [&](uint64_t *bar) {          // my TMEM stores are visible to the MMA issuer after this
                 tc_wait_st();
                 tc_fence_before();
@@ -547,8 +564,11 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             // output layer on CUDA cores: a phase of D3 units -> partial dot with w4
             auto layer3_dot = [&](auto tU0, auto tN, auto tOff, const float *r, float *ab, float acc) -> float {
                 tmem_phase(tU0, tN, tOff, IC<kUnits208 - 1>(), kColQ, nullptr, [&](int u, int h, const float (&v)[8]) {
-                    if (u == kUnits208 - 1 && h == 1) return;          // padding: w4 is zero there
-                    if (ACTS) save_half(ab, kActOff3 + 16 * u + 8 * h, v);
+                    if (u == kUnits208 - 1 && h == 1) {                 // padding: w4 is zero there
+                        if (ACTS) save_packed3(ab, u, h, v, true);
+                        return;
+                    }
+                    if (ACTS) save_packed3(ab, u, h, v, false);
 #pragma unroll
                     for (int i4 = 0; i4 < 2; ++i4) {
                         const float4 w = *reinterpret_cast<const float4 *>(r + kRecW4 + 16 * u + 8 * h + 4 * i4);     // w4 pad = 0

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
         if (lane == 0) {
             const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
             // packed A (operand-ready tiles written by the epilogue of the previous layer): one more bulk copy per k-step
-            const uint8_t *ap = p.Ap ? p.Ap + (size_t)z * p.sAp + (size_t)blockIdx.x * p.a_ksteps * kPackedStep : nullptr;
+            const uint8_t *ap = p.Ap ? p.Ap + (size_t)z * p.sAp + (size_t)blockIdx.x * p.a_tile_steps * kPackedStep : nullptr;
             for (int j = 0, s = 0, ph = 0; j < p.ksteps; ++j) {          // (stage, phase) counted, not divided: kStages is a runtime value
                 mbar_wait(&sm.empty[s], ph ^ 1);
                 TCL_EVT(true, 0, j);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                                      : p.Mul + (size_t)z * p.sMul + (size_t)mrow * p.ldmul;
         const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
         float *const Cz = p.C ? p.C + (size_t)z * p.sC : nullptr;
-        uint8_t *const cp = p.Cp ? p.Cp + (size_t)z * p.sCp + (size_t)blockIdx.x * p.c_ksteps * kPackedStep +
+        uint8_t *const cp = p.Cp ? p.Cp + (size_t)z * p.sCp + (size_t)blockIdx.x * p.c_tile_steps * kPackedStep +
                                        (size_t)(t >> 3) * 256 + (size_t)(t & 7) * 16 : nullptr;
         const float *app = (p.app && row_ok) ? p.app + (size_t)row * p.app_ld : nullptr;       // appended input columns (skip connection)
         const int app_hot = p.app_onehot ? (int)(row % p.app_w) : -1;
@@ -277,7 +277,9 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                     for (int e = 0; e < 16; ++e) aux[e] = (aux_src && (FULL || n0 + c0 + e < p.N)) ? aux_src[n0 + c0 + e] : 0.f;
                 }
             }
+            TCL_EVT(threadIdx.x == 0, 11, c0 >> 4);
             tc_wait_ld();
+            TCL_EVT(threadIdx.x == 0, 12, c0 >> 4);
             if (!row_ok) return;
             float o[16], dv[16];
 #pragma unroll
@@ -296,17 +298,29 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                         x += aux[e];
                         if (p.mode == kModeSoftplus) {
                             // softplus(beta = 100) and its derivative in log2 units: u = 100 log2(e) x
+                            // log2(1 + 2^-|u|) by a degree-6 polynomial in 2^-|u| on the FMA pipe (the fused kernels' scheme) on
+                            // every other element, by the second MUFU on the rest: the pass is bound by the MUFU pipe
                             const float u = x * kS;
                             float ex, lg;
                             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-fabsf(u)));
-                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + ex));
+                            if (e & 1) {
+                                float pl = fmaf(ex, -0.02645743577f, 0.1234514468f);
+                                pl = fmaf(pl, ex, -0.2795380944f);
+                                pl = fmaf(pl, ex, 0.4582707841f);
+                                pl = fmaf(pl, ex, -0.7182819141f);
+                                pl = fmaf(pl, ex, 1.442553145f);
+                                lg = pl * ex;
+                            } else {
+                                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + ex));
+                            }
                             x = (fmaxf(u, 0.0f) + lg) * (1.0f / kS);
-                            dv[e] = __fdividef(u >= 0.f ? 1.0f : ex, 1.0f + ex);
+                            if (p.Dv) dv[e] = __fdividef(u >= 0.f ? 1.0f : ex, 1.0f + ex);
                         }
                     }
                 }
                 o[e] = x;
             }
+            TCL_EVT(threadIdx.x == 0, 13, c0 >> 4);
             if (cp && ((n0 + c0) >> 4) < p.c_ksteps) {
                 // operand-ready output: this unit is k-step (n0 + c0) / 16 of the next layer's A tile, fp16 hi | lo, core-matrix order
                 uint32_t hi[8], lo[8];
@@ -318,12 +332,14 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 *reinterpret_cast<uint4 *>(dst + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 *reinterpret_cast<uint4 *>(dst + 4096 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
+            TCL_EVT(threadIdx.x == 0, 14, c0 >> 4);
             if (p.Dv && (p.blocked || p.dv_blocked)) {
                 float *db = p.Dv + (size_t)blockIdx.x * p.lddv * 128 + (size_t)(n0 + c0) * 128 + t;
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     if (FULL || n0 + c0 + e < p.N) db[e * 128] = dv[e];
             }
+            TCL_EVT(threadIdx.x == 0, 15, c0 >> 4);
             if (!Cz) return;
             if (p.blocked) {
                 float *cb = Cz + (size_t)blockIdx.x * p.ldc * 128 + (size_t)(n0 + c0) * 128 + t;
@@ -396,19 +412,20 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, int ldw, int N, 
     }
 }
 
-int choose_nt(int N)
+int choose_nt(int N, int max_nt)
 {
-    // as few tiles of <= 256 columns as possible, equally wide (277 -> 2 x 144, not 256 + 21), rounded up to 16
-    const int tiles = (N + kMaxNt - 1) / kMaxNt;
+    // as few tiles of <= max_nt columns as possible, equally wide (277 -> 2 x 144, not 256 + 21), rounded up to 16
+    const int tiles = (N + max_nt - 1) / max_nt;
     return ((N + tiles - 1) / tiles + 15) / 16 * 16;
 }
 
 int PackedLinear::pack(const float *W_dev, int ldw, int N_, int K_, int n_off, int k_off, bool transpose, float scale,
                        cudaStream_t stream, int sets_, long long w_set_stride, const float *k_scale_dev, long long k_scale_stride,
-                       int n_extra_)
+                       int n_extra_, int max_nt)
 {
     N = N_; K = K_; n_extra = n_extra_;
-    Nt = choose_nt(N + n_extra);
+    if (max_nt <= 0 || max_nt > kMaxNt) max_nt = kMaxNt;
+    Nt = choose_nt(N + n_extra, max_nt);
     n_tiles = (N + n_extra + Nt - 1) / Nt;
     ksteps = (K + 15) / 16;
     sets = sets_ > 0 ? sets_ : 1;
@@ -445,6 +462,8 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
         const int last = p.batch - 1, need = (last < 2 * p.w_pairs ? (last >> 1) : last - p.w_pairs) + 1;
         NPHM_REQUIRE(need <= w.sets, "tc_linear: batch of %d needs %d weight sets, %d packed", p.batch, need, w.sets);
     }
+    if (p.a_tile_steps <= 0) p.a_tile_steps = p.a_ksteps;
+    if (p.c_tile_steps <= 0) p.c_tile_steps = p.c_ksteps;
     p.W = w.slabs.as<uint8_t>();
     p.w_stride = (long long)w.set_bytes;
     p.N = w.N; p.Nt = w.Nt; p.ksteps = w.ksteps;

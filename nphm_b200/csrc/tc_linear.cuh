@@ -25,6 +25,7 @@ struct LinearParams {
     // the next launch takes it as Ap with one bulk copy per k-step and no conversion work in its main loop.
     const uint8_t *Ap = nullptr; int a_ksteps = 0; long long sAp = 0;        // replaces A1 / A2; 16 a_ksteps = packed K
     uint8_t *Cp = nullptr; int c_ksteps = 0; long long sCp = 0;              // optional, in addition to / instead of C
+    int a_tile_steps = 0, c_tile_steps = 0;                  // pitch between the tiles in k-steps (default: a_ksteps / c_ksteps)
     // columns appended behind the layer's N outputs in Cp (the next layer's `cat([h, xyz])`): app[row][0..app_w) or, one-hot,
     // e_{row mod app_w} (the tangent seeds of a forward-mode pass)
     const float *app = nullptr; int app_ld = 0, app_w = 0, app_onehot = 0;
@@ -46,7 +47,7 @@ struct PackedLinear {
     // n_extra: output columns reserved behind N in the tiling (LinearParams::app)
     int pack(const float *W_dev, int ldw, int N, int K, int n_off, int k_off, bool transpose, float scale, cudaStream_t stream,
              int sets = 1, long long w_set_stride = 0, const float *k_scale_dev = nullptr, long long k_scale_stride = 0,
-             int n_extra = 0);
+             int n_extra = 0, int max_nt = 0);      // max_nt: widest output tile (default 256); narrower = more CTAs for few rows
     int packed_ksteps_out() const { return (N + n_extra + 15) / 16; }       // k-steps of the packed output (Cp) of this layer
     int n_extra = 0;
 };

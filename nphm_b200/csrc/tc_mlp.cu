@@ -394,9 +394,12 @@ int tc_mlp_launch(nphm_mlp *h, const float *xyz, const float *cvec, int n_querie
     NPHM_REQUIRE(h->tc_ready, "tcgen05 MLP kernel: weights not packed");
     int rc;
     if ((rc = h->tc_consts.reserve((size_t)n_queries * tcm::kRecFloats * sizeof(float)))) return rc;
-    tcm::mlp_records_kernel<<<n_queries, 256, 0, stream>>>(cvec, h->dims.cvec_stride, h->tc_coff.as<int>(), h->weights.W[0].as<float>(),
-                                                          h->weights.W[6].as<float>(), h->tc_consts.as<float>());
-    NPHM_CUDA_CHECK(cudaGetLastError());
+    if (!h->tc_records_fresh) {
+        tcm::mlp_records_kernel<<<n_queries, 256, 0, stream>>>(cvec, h->dims.cvec_stride, h->tc_coff.as<int>(),
+                                                              h->weights.W[0].as<float>(), h->weights.W[6].as<float>(),
+                                                              h->tc_consts.as<float>());
+        NPHM_CUDA_CHECK(cudaGetLastError());
+    }
     tcm::Params p{h->tc_weights.as<uint8_t>(), h->tc_consts.as<float>(), xyz, n_points, n_queries, out, h->tc_live};
     const long long n_tiles = ceil_div(n_points, 64) * n_queries;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());

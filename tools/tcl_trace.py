@@ -50,9 +50,13 @@ def main():
     print('CTA start -> after alloc/sync: %d cycles' % (t[10, 1] - t0))
     print('%4s ' % 'j' + ' '.join('%11s' % s for s in names))
     for j in range(40):
-        if t[4, j] == 0:
+        if t[3, j] == 0:
             break
         print('%4d ' % j + ' '.join('%11d' % (t[f, j] - t0) for f in range(9)))
+    print('epilogue units of thread 0 (cycles from CTA start): top, accumulator loaded, computed, packed stored, derivative stored')
+    for u in range(0, 16, 2):
+        if t[11, u]:
+            print('  unit %2d ' % u + ' '.join('%8d' % (t[f, u] - t0) for f in (11, 12, 13, 14, 15)))
     print('epilogue: wait d_ready from %d to %d, done %d' % (t[9, 0] - t0, t[9, 1] - t0, t[9, 2] - t0))
 
 
