@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) fit_upstream_kernel(const Dims d, const B
 
 // one CTA per (128-point tile, member): g_s-weighted sums of delta0 / delta2 over the points (-> acc) and (POINTS) the gradient
 // w.r.t. every point through the member's local coordinates.  The deltas come operand-ready from the GEMMs (packed: per k-step
-// of 16 features [128 x 16 fp16 hi | 128 x 16 fp16 lo], value = hi + lo); thread = (point, 8 of the 16 features of a k-step).
+// of 16 features [128 x 16 fp16 hi | 128 x 16 fp16 lo], value = hi + lo).
 constexpr int kReduceThreads = 256;
 constexpr float kDeltaScale = 64.0f;          // the GEMMs carry the deltas per unit upstream gradient, times this power of two: the
                                               // fp16 hi/lo operand split needs O(1) magnitudes (g_s itself is ~1e-4 / n_points)
@@ -297,14 +297,24 @@ __global__ void __launch_bounds__(kReduceThreads) fit_reduce_kernel(const Dims d
                                                                    const uint8_t *__restrict__ packed, long long tiles,
                                                                    const float *__restrict__ gs)
 {
+    // A k-step of a packed tile is [row / 8][feature / 8][row % 8][feature % 8] fp16, hi then lo (4 KB each).  Warp (g, ch) reads,
+    // per pass, the 128 contiguous bytes of row group 4 i + g, feature half ch: lane = (row % 8) * 4 + pair of features - every
+    // load is one full line; a thread owns 2 features and, per k-step, 4 rows (one per pass).
     __shared__ float s_sum[2][kStepsH * 16];
     __shared__ float s_w[2][kStepsH * 16][3];
-    const int lane = threadIdx.x & 31;
-    const int r = threadIdx.x >> 1, ch = threadIdx.x & 1;
+    __shared__ float s_up[128];
+    __shared__ float s_g[2][128][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp & 3, ch = warp >> 2, r8 = lane >> 2, pr = lane & 3;
     const int m = blockIdx.y;
     const int set = m < 2 * d.n_symm ? (m >> 1) : m - d.n_symm;
-    const long long row = (long long)blockIdx.x * 128 + r;
+    const long long row0 = (long long)blockIdx.x * 128;
     for (int i = threadIdx.x; i < 2 * kStepsH * 16; i += blockDim.x) (&s_sum[0][0])[i] = 0.f;
+    // upstream gradient of s_m per point (zero beyond the last point: the padding rows of a tile hold garbage)
+    if (threadIdx.x < 128) {
+        const long long row = row0 + threadIdx.x;
+        s_up[threadIdx.x] = row < b.n ? gs[(size_t)m * tiles * 128 + row] * (1.0f / kDeltaScale) : 0.f;
+    }
     if (POINTS) {
         const int in0 = 3 + d.C;
         const float *W0 = w.W[0] + (size_t)set * d.H * in0;
@@ -316,54 +326,67 @@ __global__ void __launch_bounds__(kReduceThreads) fit_reduce_kernel(const Dims d
         }
     }
     __syncthreads();
-    // upstream gradient of s_m at this thread's point (zero beyond the last point: the padding rows of a tile hold garbage)
-    const float up = row < b.n ? gs[(size_t)m * tiles * 128 + row] * (1.0f / kDeltaScale) : 0.f;
+    float up[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) up[i] = s_up[(4 * i + g) * 8 + r8];
     const uint8_t *tile = packed + ((size_t)m * tiles + blockIdx.x) * kPackedPerTile * 8192;
-    const size_t off = (size_t)(r >> 3) * 256 + (size_t)ch * 128 + (size_t)(r & 7) * 16;
-    float g[3] = {0.f, 0.f, 0.f};
+    float gp[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gp[i][0] = gp[i][1] = gp[i][2] = 0.f;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
         const uint8_t *blk = tile + (size_t)(which ? 0 : kStepsH + kStepsN1) * 8192;       // delta2 first block, delta0 last
+#pragma unroll 1
         for (int j = 0; j < kStepsH; ++j) {
-            float v[8];
-            if (up != 0.f) {
-                const uint4 hq = *reinterpret_cast<const uint4 *>(blk + (size_t)j * 8192 + off);
-                const uint4 lq = *reinterpret_cast<const uint4 *>(blk + (size_t)j * 8192 + 4096 + off);
-                const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
+            const int f = j * 16 + ch * 8 + pr * 2;
+            float wa[3] = {0.f, 0.f, 0.f}, wb[3] = {0.f, 0.f, 0.f};
+            if (POINTS) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&hw[i]));
-                    const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&lw[i]));
-                    v[2 * i] = up * (a.x + c.x); v[2 * i + 1] = up * (a.y + c.y);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                for (int a = 0; a < 3; ++a) { wa[a] = s_w[which][f][a]; wb[a] = s_w[which][f + 1][a]; }
             }
-            const int f0 = j * 16 + ch * 8;
+            float c0 = 0.f, c1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float x = v[i];
-#pragma unroll
-                for (int o = 2; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane < 2 && x != 0.f) atomicAdd(&s_sum[which][f0 + i], x);
+            for (int i = 0; i < 4; ++i) {
+                const uint8_t *src = blk + (size_t)j * 8192 + (size_t)(4 * i + g) * 256 + (size_t)ch * 128 + (size_t)lane * 4;
+                const uint32_t hw = *reinterpret_cast<const uint32_t *>(src), lw = *reinterpret_cast<const uint32_t *>(src + 4096);
+                const float2 hv = __half22float2(*reinterpret_cast<const __half2 *>(&hw));
+                const float2 lv = __half22float2(*reinterpret_cast<const __half2 *>(&lw));
+                // (an all-zero upstream row may hold NaN garbage in the padding rows of the last tile: select, do not multiply)
+                const float v0 = up[i] != 0.f ? up[i] * (hv.x + lv.x) : 0.f, v1 = up[i] != 0.f ? up[i] * (hv.y + lv.y) : 0.f;
+                c0 += v0; c1 += v1;
                 if (POINTS) {
-                    g[0] = fmaf(s_w[which][f0 + i][0], v[i], g[0]);
-                    g[1] = fmaf(s_w[which][f0 + i][1], v[i], g[1]);
-                    g[2] = fmaf(s_w[which][f0 + i][2], v[i], g[2]);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) gp[i][a] = fmaf(wa[a], v0, fmaf(wb[a], v1, gp[i][a]));
                 }
+            }
+            // sum over the 8 rows of the group (lane bits 2..4), then over the row groups through shared memory
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+            if (lane < 4) {
+                if (c0 != 0.f) atomicAdd(&s_sum[which][f], c0);
+                if (c1 != 0.f) atomicAdd(&s_sum[which][f + 1], c1);
             }
         }
     }
     if (POINTS) {
+        // per row: sum over the feature pairs of the lane quad, then over the two feature halves (warps ch = 0, 1)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) g[a] += __shfl_xor_sync(0xffffffffu, g[a], 1);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v = gp[i][a];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (pr == 0) s_g[ch][(4 * i + g) * 8 + r8][a] = v;
+            }
+        __syncthreads();
         const bool mirror = (m & 1) && m < 2 * d.n_symm;
-        if (mirror) g[0] = -g[0];
-        if (ch == 0 && row < b.n) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                if (g[a] != 0.f) atomicAdd(b.grad_points + row * 3 + a, g[a]);
+        for (int i = threadIdx.x; i < 128 * 3; i += blockDim.x) {
+            const int pt = i / 3, a = i % 3;
+            float v = s_g[0][pt][a] + s_g[1][pt][a];
+            if (a == 0 && mirror) v = -v;
+            const long long row = row0 + pt;
+            if (row < b.n && v != 0.f) atomicAdd(b.grad_points + row * 3 + a, v);
         }
     }
     __syncthreads();

@@ -38,20 +38,26 @@ constexpr int kPackedStep = 2 * 128 * 32;       // bytes of one k-step of a pack
 constexpr int kAPitch = 20;                      // floats per staged fp32 row (16 + 4: 80-byte pitch spreads the banks)
 constexpr int kADepth = 3;                       // k-steps of A kept in flight per thread (cp.async groups)
 // dynamic shared memory: [Ctl | stages x (a_hi 4 KB | a_lo 4 KB | b Nt*64) | a32 ring]
+constexpr int kMulSlots = 5;                     // ring of multiplier units (16 features x 128 rows fp32 = 8 KB) in the a32 space
 struct __align__(128) Ctl {
     uint64_t a_full[kMaxStages], b_full[kMaxStages], empty[kMaxStages], d_ready;
+    uint64_t mul_full[kMulSlots], mul_empty[kMulSlots];
     uint32_t tmem_base;
 };
-constexpr int kCtlBytes = 128;
+constexpr int kCtlBytes = 256;
+static_assert(kMulSlots * 16 * 128 * 4 <= kARing * 128 * kAPitch * 4, "multiplier ring must fit the fp32 staging area of A");
 static_assert(sizeof(Ctl) <= kCtlBytes, "control block");
 constexpr int kA32Bytes = kARing * 128 * kAPitch * 4;
 __host__ __device__ inline int stage_bytes(int Nt) { return 2 * 128 * 32 + Nt * 64; }
 inline int smem_bytes(int Nt, int stages) { return kCtlBytes + stages * stage_bytes(Nt) + kA32Bytes; }
 
 #ifdef NPHM_TCL_TRACE
+#ifndef NPHM_TCL_TRACE_NT
+#define NPHM_TCL_TRACE_NT 128          // which tile width to record (the chain uses 128, the fitting backward 208 / 112)
+#endif
 // timeline of CTA (0,0,0): [role field][k-step] clock64 stamps (tools/tcl_trace.py)
 __device__ long long g_tcl_trace[16 * 64];
-#define TCL_EVT(cond, field, j) do { if ((cond) && p.Nt == 256 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) \
+#define TCL_EVT(cond, field, j) do { if ((cond) && p.Nt == NPHM_TCL_TRACE_NT && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64) \
     g_tcl_trace[(field) * 64 + (j)] = clock64(); } while (0)
 #else
 #define TCL_EVT(cond, field, j) do { } while (0)
@@ -94,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sm.a_full[i], kRowWarps); mbar_init(&sm.b_full[i], 1); mbar_init(&sm.empty[i], 1); }
         mbar_init(&sm.d_ready, 1);
+        for (int i = 0; i < kMulSlots; ++i) { mbar_init(&sm.mul_full[i], 1); mbar_init(&sm.mul_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kRowWarps + 1) {
@@ -108,9 +115,29 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     const int slab_bytes = p.Nt * 64;
     TCL_EVT(threadIdx.x == 0, 10, 1);
 
+    // MULT epilogue with a blocked multiplier and packed A (the fp32 staging ring of A is idle then): the producer streams the
+    // multiplier, unit by unit (16 features x 128 rows = 8 KB contiguous), into that ring while the MMAs run - read from global
+    // memory inside the epilogue, every unit cost a full memory round trip (measured: 5 k cycles per unit)
+    const bool mul_ring = p.Ap && p.mode == kModeMult && p.Mul && (p.blocked || p.mul_blocked) && p.mul_div == 1;
+    const int n_units = p.Nt / 16;
+    float (*mring)[16][128] = reinterpret_cast<float (*)[16][128]>(a32);
+    auto unit_in_ring = [&](int u) { return mul_ring && n0 + 16 * u + 16 <= p.ldmul; };     // whole unit inside the tile's block
+
     if (warp == kRowWarps) {
         // ================================================================ producer: weight slabs (bulk async copies)
         if (lane == 0) {
+            const float *mul_tile = mul_ring ? p.Mul + (size_t)z * p.sMul + (size_t)blockIdx.x * p.ldmul * 128 + (size_t)n0 * 128 : nullptr;
+            int mu = 0;                                    // next multiplier unit to fetch
+            auto fetch_mul = [&](int limit) {
+                for (; mu < limit && mu < n_units; ++mu) {
+                    if (!unit_in_ring(mu)) continue;
+                    const int slot = mu % kMulSlots;
+                    mbar_wait(&sm.mul_empty[slot], ((mu / kMulSlots) & 1) ^ 1);
+                    mbar_expect_tx(&sm.mul_full[slot], 16 * 128 * 4);
+                    bulk_g2s(&mring[slot][0][0], mul_tile + (size_t)mu * 16 * 128, 16 * 128 * 4, &sm.mul_full[slot]);
+                }
+            };
+            fetch_mul(kMulSlots);                          // the first units travel while the MMAs run
             const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
             // packed A (operand-ready tiles written by the epilogue of the previous layer): one more bulk copy per k-step
             const uint8_t *ap = p.Ap ? p.Ap + (size_t)z * p.sAp + (size_t)blockIdx.x * p.a_tile_steps * kPackedStep : nullptr;
@@ -122,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 if (ap) bulk_g2s(st_a_hi(s), ap + (size_t)j * kPackedStep, kPackedStep, &sm.b_full[s]);   // a_hi | a_lo are adjacent
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
+            fetch_mul(n_units);                            // the rest as the epilogue frees the slots
         }
     } else if (warp == kRowWarps + 1) {
         // ================================================================ MMA issuer (whole warp runs the loop, one lane issues)
@@ -261,7 +289,15 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             uint32_t r[16];
             tc_ld16(tl + c0, r);
             float aux[16];
-            if (row_ok) {
+            const int unit = c0 >> 4;
+            if (unit_in_ring(unit)) {
+                const int slot = unit % kMulSlots;
+                mbar_wait(&sm.mul_full[slot], (unit / kMulSlots) & 1);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) aux[e] = mring[slot][e][t];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.mul_empty[slot]);
+            } else if (row_ok) {
                 if (aux_blk) {
                     const float *ab = aux_src ? aux_src + (size_t)(n0 + c0) * 128 : nullptr;
 #pragma unroll
