@@ -38,18 +38,23 @@ constexpr int kPackedStep = 2 * 128 * 32;       // bytes of one k-step of a pack
 constexpr int kAPitch = 20;                      // floats per staged fp32 row (16 + 4: 80-byte pitch spreads the banks)
 constexpr int kADepth = 3;                       // k-steps of A kept in flight per thread (cp.async groups)
 // dynamic shared memory: [Ctl | stages x (a_hi 4 KB | a_lo 4 KB | b Nt*64) | a32 ring]
-constexpr int kMulSlots = 5;                     // ring of multiplier units (16 features x 128 rows fp32 = 8 KB) in the a32 space
+#ifndef NPHM_TCL_MULSLOTS
+#define NPHM_TCL_MULSLOTS 3
+#endif
+constexpr int kMulSlots = NPHM_TCL_MULSLOTS;                     // ring of multiplier units (16 features x 128 rows fp32 = 8 KB) in the a32 space
 struct __align__(128) Ctl {
     uint64_t a_full[kMaxStages], b_full[kMaxStages], empty[kMaxStages], d_ready;
-    uint64_t mul_full[kMulSlots], mul_empty[kMulSlots];
+    uint64_t mul_full[kMaxNt / 16], mul_empty[kMaxNt / 16];       // one single-use pair per 16-column unit (no phase bookkeeping)
     uint32_t tmem_base;
 };
-constexpr int kCtlBytes = 256;
+constexpr int kCtlBytes = 512;
 static_assert(kMulSlots * 16 * 128 * 4 <= kARing * 128 * kAPitch * 4, "multiplier ring must fit the fp32 staging area of A");
 static_assert(sizeof(Ctl) <= kCtlBytes, "control block");
 constexpr int kA32Bytes = kARing * 128 * kAPitch * 4;
 __host__ __device__ inline int stage_bytes(int Nt) { return 2 * 128 * 32 + Nt * 64; }
-inline int smem_bytes(int Nt, int stages) { return kCtlBytes + stages * stage_bytes(Nt) + kA32Bytes; }
+constexpr int kMulRingBytes = kMulSlots * 16 * 128 * 4;
+// behind the operand stages: the fp32 staging ring of A, or (packed A: no staging) just the multiplier ring
+inline int smem_bytes(int Nt, int stages, bool packed_a) { return kCtlBytes + stages * stage_bytes(Nt) + (packed_a ? kMulRingBytes : kA32Bytes); }
 
 #ifdef NPHM_TCL_TRACE
 #ifndef NPHM_TCL_TRACE_NT
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sm.a_full[i], kRowWarps); mbar_init(&sm.b_full[i], 1); mbar_init(&sm.empty[i], 1); }
         mbar_init(&sm.d_ready, 1);
-        for (int i = 0; i < kMulSlots; ++i) { mbar_init(&sm.mul_full[i], 1); mbar_init(&sm.mul_empty[i], 4); }
+        for (int i = 0; i < kMaxNt / 16; ++i) { mbar_init(&sm.mul_full[i], 1); mbar_init(&sm.mul_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kRowWarps + 1) {
@@ -132,12 +137,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 for (; mu < limit && mu < n_units; ++mu) {
                     if (!unit_in_ring(mu)) continue;
                     const int slot = mu % kMulSlots;
-                    mbar_wait(&sm.mul_empty[slot], ((mu / kMulSlots) & 1) ^ 1);
-                    mbar_expect_tx(&sm.mul_full[slot], 16 * 128 * 4);
-                    bulk_g2s(&mring[slot][0][0], mul_tile + (size_t)mu * 16 * 128, 16 * 128 * 4, &sm.mul_full[slot]);
+                    if (mu >= kMulSlots) mbar_wait(&sm.mul_empty[mu - kMulSlots], 0);      // the unit that held this slot is consumed
+                    mbar_expect_tx(&sm.mul_full[mu], 16 * 128 * 4);
+                    bulk_g2s(&mring[slot][0][0], mul_tile + (size_t)mu * 16 * 128, 16 * 128 * 4, &sm.mul_full[mu]);
                 }
             };
-            fetch_mul(kMulSlots);                          // the first units travel while the MMAs run
             const uint8_t *w = p.W + (size_t)wset * p.w_stride + (size_t)nt_idx * p.ksteps * slab_bytes;
             // packed A (operand-ready tiles written by the epilogue of the previous layer): one more bulk copy per k-step
             const uint8_t *ap = p.Ap ? p.Ap + (size_t)z * p.sAp + (size_t)blockIdx.x * p.a_tile_steps * kPackedStep : nullptr;
@@ -148,6 +152,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 bulk_g2s(st_b(s), w + (size_t)j * slab_bytes, slab_bytes, &sm.b_full[s]);
                 if (ap) bulk_g2s(st_a_hi(s), ap + (size_t)j * kPackedStep, kPackedStep, &sm.b_full[s]);   // a_hi | a_lo are adjacent
                 if (++s == kStages) { s = 0; ph ^= 1; }
+                if (j == kStages - 1 || j == p.ksteps - 1) fetch_mul(kMulSlots);   // behind the first operand stages: the first
+                                                                                   // multiplier units travel while the MMAs run
             }
             fetch_mul(n_units);                            // the rest as the epilogue frees the slots
         }
@@ -292,11 +298,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
             const int unit = c0 >> 4;
             if (unit_in_ring(unit)) {
                 const int slot = unit % kMulSlots;
-                mbar_wait(&sm.mul_full[slot], (unit / kMulSlots) & 1);
+                mbar_wait(&sm.mul_full[unit], 0);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) aux[e] = mring[slot][e][t];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.mul_empty[slot]);
+                if (lane == 0) mbar_arrive(&sm.mul_empty[unit]);
             } else if (row_ok) {
                 if (aux_blk) {
                     const float *ab = aux_src ? aux_src + (size_t)(n0 + c0) * 128 : nullptr;
@@ -507,10 +513,18 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
     if (p.mul_div <= 0) p.mul_div = 1;
     // three operand stages leave room for two CTAs per SM (the epilogue of one overlaps the main loop of the other); wide tiles
     // and single launches of few tiles keep four
-    p.stages = (smem_bytes(p.Nt, 3) <= 112 * 1024 && ceil_div(p.M, 128) * w.n_tiles * p.batch > 148) ? 3 : kMaxStages;
-    const int smem = smem_bytes(p.Nt, p.stages);
+    // two CTAs per SM when there are enough tiles (the epilogue of one overlaps the main loop of the other): as many operand
+    // stages as fit in half of the shared memory, at least three; otherwise four stages, one CTA per SM
+    const bool packed_a = p.Ap != nullptr;
+    const bool many = ceil_div(p.M, 128) * w.n_tiles * p.batch > 148;
+    p.stages = kMaxStages;
+#ifdef NPHM_TCL_FORCE3
+    if (packed_a) p.stages = 3;
+#endif
+    if (many && smem_bytes(p.Nt, kMaxStages, packed_a) > 112 * 1024 && smem_bytes(p.Nt, 3, packed_a) <= 112 * 1024) p.stages = 3;
+    const int smem = smem_bytes(p.Nt, p.stages, packed_a);
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes(kMaxNt, kMaxStages)));
+                                         smem_bytes(kMaxNt, kMaxStages, false)));
     dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)w.n_tiles, (unsigned)p.batch);
     linear_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
