@@ -14,8 +14,8 @@ timeout 100 python tools/mc_time.py > gpurun_out/mc_time_$T.txt 2>&1
 # launch lists (shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$T.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-stock-gpu > gpurun_out/launches_$T.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_joint_$T.csv \
-    python tools/bench_joint.py --steps 4 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_joint_$T.csv \
+    python tools/bench_joint.py --steps 3 > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_fit_$T.csv \
     python tools/bench_fit.py --steps 4 > /dev/null 2>&1
 # full captures: dense ensemble kernel (one launch of the bench workload), the three marching-cubes kernels, the generic linear layer
