@@ -7,7 +7,7 @@ gpurun-ignored, so the byte-identical files travel to the GPU box, where ``/root
 
 What is copied (verbatim, ``shutil.copyfile``; a SHA-256 manifest is written next to them):
   src/NPHM/__init__.py
-  src/NPHM/models/{EnsembledDeepSDF,deepSDF,reconstruction,fitting,iterative_root_finding,diff_operators}.py
+  src/NPHM/models/{EnsembledDeepSDF,deepSDF,reconstruction,fitting,iterative_root_finding,diff_operators,loss_functions}.py
   src/NPHM/utils/reconstruction.py
   assets/{anchors_39,nphm_lat_mean,nphm_lat_std}.npy
 Nothing else of the reference is needed for SURVEY.md section 8's path.  ``oracle/ref_loader.py`` imports them.
@@ -30,6 +30,7 @@ FILES = [
     'src/NPHM/models/fitting.py',
     'src/NPHM/models/iterative_root_finding.py',
     'src/NPHM/models/diff_operators.py',
+    'src/NPHM/models/loss_functions.py',
     'src/NPHM/utils/reconstruction.py',
     'assets/anchors_39.npy',
     'assets/nphm_lat_mean.npy',

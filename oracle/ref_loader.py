@@ -68,6 +68,10 @@ def load():
         for name in _MODULES:
             mod = importlib.import_module('NPHM.' + name)
             setattr(ns, name.split('.')[-1] if not name.startswith('utils.') else 'utils_reconstruction', mod)
+        # the identity-space training losses: optional, older prebuilt copies do not carry the file
+        ns.loss_functions = None
+        if os.path.exists(os.path.join(src, 'NPHM', 'models', 'loss_functions.py')):
+            ns.loss_functions = importlib.import_module('NPHM.models.loss_functions')
     finally:
         sys.path.remove(src)
         for k in [k for k in sys.modules if k == 'NPHM' or k.startswith('NPHM.') or k in _STUBS]:
