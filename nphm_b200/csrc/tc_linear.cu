@@ -518,9 +518,6 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
     const bool packed_a = p.Ap != nullptr;
     const bool many = ceil_div(p.M, 128) * w.n_tiles * p.batch > 148;
     p.stages = kMaxStages;
-#ifdef NPHM_TCL_FORCE3
-    if (packed_a) p.stages = 3;
-#endif
     if (many && smem_bytes(p.Nt, kMaxStages, packed_a) > 112 * 1024 && smem_bytes(p.Nt, 3, packed_a) <= 112 * 1024) p.stages = 3;
     const int smem = smem_bytes(p.Nt, p.stages, packed_a);
     NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
