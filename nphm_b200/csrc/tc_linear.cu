@@ -540,3 +540,46 @@ extern "C" int nphm_debug_tcl_trace(long long *host, int n_ll)
     return NPHM_OK;
 }
 #endif
+
+// Test entry (not part of the public ABI; tests/test_gpu_networks.py): three chained layers per batch entry on the generic layer,
+//   H1 = A W1^T                      row-major fp32 in  -> packed out
+//   H2 = (H1 W2^T) * Mul             packed in, blocked multiplier (streamed through the shared-memory ring) -> packed out
+//   Z  = H2 W3^T                     packed in -> row-major fp32 out
+// a [batch][M][K], w1 [sets][N1][K], w2 [sets][N2][N1], w3 [sets][N3][N2], mul [batch][ceil(M/128)][N2 rounded up to 4][128],
+// z [batch][M][N3]; batch entry b uses weight set b/2 for b < 2 w_pairs, b - w_pairs beyond.
+extern "C" int nphm_debug_linear_chain(const float *a_dev, const float *w1_dev, const float *w2_dev, const float *w3_dev,
+                                       const float *mul_dev, int batch, int w_pairs, long long M, int K, int N1, int N2, int N3,
+                                       float *z_dev, void *stream_)
+{
+    using namespace nphm;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NPHM_REQUIRE(a_dev && w1_dev && w2_dev && w3_dev && mul_dev && z_dev && batch >= 1 && M > 0, "nphm_debug_linear_chain: bad arguments");
+    const int sets = batch - w_pairs;
+    tcl::PackedLinear l1, l2, l3;
+    int rc;
+    if ((rc = l1.pack(w1_dev, K, N1, K, 0, 0, false, 1.0f, stream, sets, (long long)N1 * K)) ||
+        (rc = l2.pack(w2_dev, N1, N2, N1, 0, 0, false, 1.0f, stream, sets, (long long)N2 * N1)) ||
+        (rc = l3.pack(w3_dev, N2, N3, N2, 0, 0, false, 1.0f, stream, sets, (long long)N3 * N2))) return rc;
+    const long long tiles = ceil_div(M, 128);
+    const int ks1 = l1.packed_ksteps_out(), ks2 = l2.packed_ksteps_out(), ldm = (N2 + 3) / 4 * 4;
+    DeviceBuffer h1, h2;
+    if ((rc = h1.reserve((size_t)batch * tiles * ks1 * 8192)) || (rc = h2.reserve((size_t)batch * tiles * ks2 * 8192))) return rc;
+    tcl::LinearParams p{};
+    p.M = M; p.batch = batch; p.w_pairs = w_pairs;
+    p.A1 = a_dev; p.lda1 = K; p.K1 = K; p.sA1 = M * K;
+    p.mode = tcl::kModeLinear; p.Cp = h1.as<uint8_t>(); p.c_ksteps = ks1; p.sCp = tiles * ks1 * 8192;
+    if ((rc = tcl::launch_linear(l1, p, stream))) return rc;
+    p = tcl::LinearParams{};
+    p.M = M; p.batch = batch; p.w_pairs = w_pairs;
+    p.Ap = h1.as<uint8_t>(); p.a_ksteps = ks1; p.sAp = tiles * ks1 * 8192;
+    p.mode = tcl::kModeMult; p.Mul = mul_dev; p.ldmul = ldm; p.mul_blocked = 1; p.sMul = tiles * 128 * ldm;
+    p.Cp = h2.as<uint8_t>(); p.c_ksteps = ks2; p.sCp = tiles * ks2 * 8192;
+    if ((rc = tcl::launch_linear(l2, p, stream))) return rc;
+    p = tcl::LinearParams{};
+    p.M = M; p.batch = batch; p.w_pairs = w_pairs;
+    p.Ap = h2.as<uint8_t>(); p.a_ksteps = ks2; p.sAp = tiles * ks2 * 8192;
+    p.mode = tcl::kModeLinear; p.C = z_dev; p.ldc = N3; p.sC = M * N3;
+    if ((rc = tcl::launch_linear(l3, p, stream))) return rc;
+    NPHM_CUDA_CHECK(cudaStreamSynchronize(stream));          // the temporaries above are freed on return
+    return NPHM_OK;
+}

@@ -311,3 +311,44 @@ def test_npm_width_deepsdf_matches_reference_golden(cuda_device):
     err2 = float((out2.cpu() - torch.from_numpy(g['out_plain'])).abs().max())
     print('plain-init 1024 x 8, 3 outputs: max abs err %.3g (range of the golden %.3g)' % (err2, float(np.ptp(g['out_plain']))))
     assert err2 < TOL
+
+
+def test_generic_linear_layer_packed_blocked_batched(cuda_device):
+    """tc_linear.cu through its test entry: three chained layers per batch entry - row-major in -> packed -> (x blocked
+    multiplier, streamed through the shared-memory ring) -> packed -> row-major out - batched over entries that share weight
+    sets pairwise, rows not a multiple of the 128-row tile.  Against float64 torch."""
+    import ctypes
+    from nphm_b200 import _native
+    lib = _native.lib()
+    rng = np.random.RandomState(3)
+    batch, pairs, M, K, N1, N2, N3 = 5, 2, 300, 40, 200, 101, 24
+    sets = batch - pairs
+    a = torch.from_numpy(rng.randn(batch, M, K).astype(np.float32)).to(cuda_device)
+    w1 = torch.from_numpy((rng.randn(sets, N1, K) / np.sqrt(K)).astype(np.float32)).to(cuda_device)
+    w2 = torch.from_numpy((rng.randn(sets, N2, N1) / np.sqrt(N1)).astype(np.float32)).to(cuda_device)
+    w3 = torch.from_numpy((rng.randn(sets, N3, N2) / np.sqrt(N2)).astype(np.float32)).to(cuda_device)
+    mul = torch.from_numpy(rng.rand(batch, M, N2).astype(np.float32)).to(cuda_device)
+    tiles, ldm = (M + 127) // 128, (N2 + 3) // 4 * 4
+    blocked = torch.zeros(batch, tiles, ldm, 128, device=cuda_device)
+    padded = torch.zeros(batch, tiles * 128, N2, device=cuda_device)
+    padded[:, :M] = mul
+    blocked[:, :, :N2, :] = padded.reshape(batch, tiles, 128, N2).permute(0, 1, 3, 2)
+    z = torch.empty(batch, M, N3, device=cuda_device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    lib.nphm_debug_linear_chain.restype = ctypes.c_int
+    lib.nphm_debug_linear_chain.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong] + \
+        [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+    rc = lib.nphm_debug_linear_chain(a.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), blocked.data_ptr(), batch, pairs,
+                                     M, K, N1, N2, N3, z.data_ptr(), stream)
+    assert rc == 0, _native.last_error() if hasattr(_native, 'last_error') else rc
+    torch.cuda.synchronize()
+    worst = 0.0
+    for b in range(batch):
+        s = b // 2 if b < 2 * pairs else b - pairs
+        h1 = a[b].double() @ w1[s].double().T
+        h2 = (h1 @ w2[s].double().T) * mul[b].double()
+        want = h2 @ w3[s].double().T
+        err = float((z[b].double() - want).abs().max() / want.abs().max())
+        worst = max(worst, err)
+    print('generic linear layer chain (packed / blocked / batched): max rel err %.2e' % worst)
+    assert worst < 5e-6            # three chained fp32-accurate layers (3-pass fp16 split: ~2^-22 per product)
