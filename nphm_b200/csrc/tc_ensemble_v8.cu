@@ -49,6 +49,7 @@ constexpr int kUnits208 = 13, kUnits112 = 7;
 constexpr int rounds(int units) { return (units + kParts - 1) / kParts; }
 constexpr int kR0b = rounds(kUnits208 - kU0a), kR1 = rounds(kUnits112), kR2 = rounds(kUnits208);
 constexpr int kE3aUnits = 7;                    // D3 columns [0,112) = the columns the next member's D1 needs
+constexpr int kM2aUnits = 7;                    // layer-2 column split: units [0,7) = columns [0,112), units [7,13) = [112,208)
 
 // Optional timeline trace (build with -DNPHM_TC_TRACE, tools/build_variant.sh): CTA 0 records clock64() at the phase
 // boundaries of its second tile - [member][event], events 0-15 compute warp 0, 16-31 MMA issuer, 32-47 compute warp 13.
@@ -65,7 +66,7 @@ struct __align__(128) Smem {
     float partial[kParts - 1][128];
     uint64_t w_full[2], w_empty[2];
     uint64_t rec_full[kRecSlots], rec_empty[kRecSlots];
-    uint64_t a0a_ready, a0b_ready[kR0b], a1_ready[kR1], a2_ready[kR2], q_lo_free, d_ready, mask_ready;
+    uint64_t a0a_ready, a0b_ready[kR0b], a1_ready[kR1], a2_ready[kR2], q_lo_free, d_ready, d2b_ready, mask_ready;
     unsigned long long maskq[2][4];
     uint32_t tmem_base;
 };
@@ -151,10 +152,16 @@ template <int V> struct IC { static constexpr int value = V; };
 #ifndef NPHM_V8_E0A_EARLY
 #define NPHM_V8_E0A_EARLY 0
 #endif
+// layer 2 as two column halves (D2 columns [0,112) first, then [112,208)): the layer-2 epilogue starts on the first half while
+// the tensor pipe still produces the second - the MMAs of the second half would otherwise be pure tail behind the layer-1 epilogue
+#ifndef NPHM_V8_M2_SPLIT
+#define NPHM_V8_M2_SPLIT 1
+#endif
 #if NPHM_V8_OFFSETS
 constexpr int kOffE3a = 0, kOffE0b = 1, kOffE3b = 3, kOffE1 = 0, kOffE2 = 0, kOffE0a = 1;
+constexpr int kOffE2b = 3;          // split layer-2 epilogue: E2a (7) + E2b (6) + E0a (6) = 5 + 5 + 5 + 4 over the four groups
 #else
-constexpr int kOffE3a = 0, kOffE0b = 0, kOffE3b = 0, kOffE1 = 0, kOffE2 = 0, kOffE0a = 0;
+constexpr int kOffE3a = 0, kOffE0b = 0, kOffE3b = 0, kOffE1 = 0, kOffE2 = 0, kOffE0a = 0, kOffE2b = 0;
 #endif
 
 template <bool PRUNE, bool ACTS>
@@ -186,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
         for (int i = 0; i < kR2; ++i) mbar_init(&sm.a2_ready[i], kEpiWarps);
         mbar_init(&sm.q_lo_free, kEpiWarps);
         mbar_init(&sm.d_ready, 1);
+        mbar_init(&sm.d2b_ready, 1);
         mbar_init(&sm.mask_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -263,6 +271,9 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             int wb = 0;
             uint32_t wph = 0, mph = 0, tcount = 0;
             const uint32_t idesc1 = make_idesc(kNP1), idesc2 = make_idesc(kNP2);
+            const uint32_t idesc2a = make_idesc(16 * kM2aUnits), idesc2b = make_idesc(kNP2 - 16 * kM2aUnits);
+            // A2 units per round of the layer-2 epilogue (= k-steps of layer 3 per a2_ready barrier)
+            constexpr int kA2Round[kR2 + 1] = {0, 4, NPHM_V8_M2_SPLIT ? kM2aUnits : 8, NPHM_V8_M2_SPLIT ? kM2aUnits + 4 : 12, kUnits208};
             // one k-step = 3 MMAs (hi*hi + hi*lo + lo*hi) on the in-place operand unit at column `a`; `b` = descriptor of
             // the slab's hi half, its lo half lies n * 32 bytes (n * 2 descriptor units) further
             auto kstep = [&](uint32_t d, uint32_t a, uint64_t b, int n, uint32_t idesc, bool fresh) {
@@ -322,10 +333,22 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
 #pragma unroll
                             for (int j = r * kParts; j < (r + 1) * kParts; ++j)
                                 if (j < kUnits112)
-                                    kstep(tmem + kColP, tmem + kColQ + 16 * j, b0 + (uint64_t)(j * (kSlabBytes >> 4)), kNP2, idesc2, j == 0);
+                                    kstep(tmem + kColP, tmem + kColQ + 16 * j, b0 + (uint64_t)(j * (kSlabBytes >> 4)), kNP2,
+                                          NPHM_V8_M2_SPLIT ? idesc2a : idesc2, j == 0);
                         }
+#if NPHM_V8_M2_SPLIT
+                        commit(&sm.d_ready);                          // D2 columns [0,112) complete
+                        // second column half: rows [112,208) of every slab (row block 14: 14 * 256 B further), D2 columns [112,208)
+#pragma unroll
+                        for (int j = 0; j < kUnits112; ++j)
+                            kstep(tmem + kColP + 16 * kM2aUnits, tmem + kColQ + 16 * j,
+                                  b0 + (uint64_t)(j * (kSlabBytes >> 4)) + (uint64_t)(16 * kM2aUnits / 8 * 256 / 16), kNP2, idesc2b, j == 0);
+                        commit(&sm.w_empty[wb]);
+                        commit(&sm.d2b_ready);
+#else
                         commit(&sm.w_empty[wb]);
                         commit(&sm.d_ready);
+#endif
                         TRACE_EVT(true, m, 22);
                         next_buf();
                     }
@@ -339,8 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                             tc_fence_after();
                             TRACE_EVT(true, m, 23 + r);
 #pragma unroll
-                            for (int j = r * kParts; j < (r + 1) * kParts; ++j) {
-                                if (j >= kUnits208) continue;
+                            for (int j = kA2Round[r]; j < kA2Round[r + 1]; ++j) {
                                 if (j == 7) {                       // second weight group (k-steps 7-12)
                                     commit(&sm.w_empty[wb]);
                                     next_buf();
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
         const int q = warp & 3, part = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);       // this warp's TMEM lane quarter
-        uint32_t d_ph = 0, tcount = 0, rcount = 0;
+        uint32_t d_ph = 0, d2_ph = 0, tcount = 0, rcount = 0;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
                 const long long tile = ACTS ? item / n_groups : item;
             int qi;
@@ -683,11 +705,21 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 d_ph ^= 1;
                 tc_fence_after();
                 TRACE_EVT(trw, m, tr0 + 5);
-                tmem_phase(IC<0>(), IC<kUnits208>(), IC<kOffE2>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready, [&](int u, int h, float (&v)[8]) {
+                auto e2_body = [&](int u, int h, float (&v)[8]) {
                     if (u == kUnits208 - 1 && h == 1) v[0] = 1.0f;          // k = 200: bias row of layer 3
                     if (ACTS) save_half(ab, kActOff2 + 16 * u + 8 * h, v);
                     store_half(tl + kColP + 16 * u, h, v);
-                });
+                };
+#if NPHM_V8_M2_SPLIT
+                tmem_phase(IC<0>(), IC<kM2aUnits>(), IC<kOffE2>(), IC<-1>(), kColP, sm.a2_ready, e2_body);
+                mbar_wait(&sm.d2b_ready, d2_ph);                              // D2 columns [112,208)
+                d2_ph ^= 1;
+                tc_fence_after();
+                tmem_phase(IC<kM2aUnits>(), IC<kUnits208 - kM2aUnits>(), IC<kOffE2b>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready + 2,
+                           e2_body);
+#else
+                tmem_phase(IC<0>(), IC<kUnits208>(), IC<kOffE2>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready, e2_body);
+#endif
                 TRACE_EVT(trw, m, tr0 + 6);
                 if (!NPHM_V8_E0A_EARLY) next_layer0_a();
                 TRACE_EVT(trw, m, tr0 + 7);
