@@ -157,11 +157,17 @@ template <int V> struct IC { static constexpr int value = V; };
 #ifndef NPHM_V8_M2_SPLIT
 #define NPHM_V8_M2_SPLIT 1
 #endif
+// layer 0 of the NEXT member's first units in two halves: one in the wait for the first layer-2 columns, one behind the layer-2
+// epilogue.  Measured SLOWER (A/B on one GPU: 360 vs 354 ms): kept as an option, off.
+#ifndef NPHM_V8_E0A_SPLIT
+#define NPHM_V8_E0A_SPLIT 0
+#endif
 #if NPHM_V8_OFFSETS
 constexpr int kOffE3a = 0, kOffE0b = 1, kOffE3b = 3, kOffE1 = 0, kOffE2 = 0, kOffE0a = 1;
 constexpr int kOffE2b = 3;          // split layer-2 epilogue: E2a (7) + E2b (6) + E0a (6) = 5 + 5 + 5 + 4 over the four groups
+constexpr int kOffE0a1 = 1, kOffE0a2 = 0;       // E0a in two halves of 3 units: groups 1-3, then groups 0-2
 #else
-constexpr int kOffE3a = 0, kOffE0b = 0, kOffE3b = 0, kOffE1 = 0, kOffE2 = 0, kOffE0a = 0, kOffE2b = 0;
+constexpr int kOffE3a = 0, kOffE0b = 0, kOffE3b = 0, kOffE1 = 0, kOffE2 = 0, kOffE0a = 0, kOffE2b = 0, kOffE0a1 = 0, kOffE0a2 = 0;
 #endif
 
 template <bool PRUNE, bool ACTS>
@@ -685,19 +691,25 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 // before the layer-1 epilogue is complete) or of the layer-3 MMAs
                 const unsigned long long rest = (m + 1 < 64) ? (mask >> (m + 1)) : 0ull;
                 a_done = rest != 0;
-                auto next_layer0_a = [&]() {
+                auto next_layer0_units = [&](auto tU0, auto tN, auto tOff, bool last) {
                     if (a_done) {
                         const uint32_t nslot = (rcount + 1) % kRecSlots;
                         mbar_wait(&sm.rec_full[nslot], ((rcount + 1) / kRecSlots) & 1);
                         const float *nrec = sm.rec[nslot];
                         float nx, ny, nz;
                         member_coords(nrec, nx, ny, nz);
-                        layer0_phase(IC<0>(), IC<kU0a>(), IC<kOffE0a>(), nrec, nx, ny, nz, kColS,
-                                     acts_of(m + 1 + (__ffsll((long long)rest) - 1)), nullptr);
-                        publish(&sm.a0a_ready);
+                        layer0_phase(tU0, tN, tOff, nrec, nx, ny, nz, kColS, acts_of(m + 1 + (__ffsll((long long)rest) - 1)), nullptr);
+                        if (last) publish(&sm.a0a_ready);
                     }
                 };
+                auto next_layer0_a = [&]() { next_layer0_units(IC<0>(), IC<kU0a>(), IC<kOffE0a>(), true); };
+#if NPHM_V8_E0A_SPLIT
+                // first half here, in the wait for the first layer-2 columns (S is free: layer 1 is complete); second half behind
+                // the layer-2 epilogue, in the shadow of the layer-3 MMAs - all of it there made the output layer wait
+                next_layer0_units(IC<0>(), IC<kU0a / 2>(), IC<kOffE0a1>(), false);
+#else
                 if (NPHM_V8_E0A_EARLY) next_layer0_a();
+#endif
                 TRACE_EVT(trw, m, tr0 + 10);
 
                 // ---------------- epilogue of layer 2: P in place
@@ -721,7 +733,11 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
                 tmem_phase(IC<0>(), IC<kUnits208>(), IC<kOffE2>(), IC<kUnits208 - 1>(), kColP, sm.a2_ready, e2_body);
 #endif
                 TRACE_EVT(trw, m, tr0 + 6);
+#if NPHM_V8_E0A_SPLIT
+                next_layer0_units(IC<kU0a / 2>(), IC<kU0a - kU0a / 2>(), IC<kOffE0a2>(), true);
+#else
                 if (!NPHM_V8_E0A_EARLY) next_layer0_a();
+#endif
                 TRACE_EVT(trw, m, tr0 + 7);
                 // ---------------- output layer, first part: D3 columns [0,112) (the columns the next member's D1 lands in)
                 mbar_wait(&sm.d_ready, d_ph);
