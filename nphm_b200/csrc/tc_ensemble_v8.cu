@@ -644,13 +644,14 @@ __global__ void __launch_bounds__(kThreads, 1) ensemble_tc_kernel_v8(const Param
             for (int m = 0; m < p.n_members; ++m) {
                 if (!((mask >> m) & 1)) continue;
                 const uint32_t rslot = rcount % kRecSlots;
+                const int tr0 = warp == 0 ? 0 : 32;
+                const bool trw = warp == 0 || warp == 13;
+                TRACE_EVT(trw, m, tr0 + 11);
                 mbar_wait(&sm.rec_full[rslot], (rcount / kRecSlots) & 1);
                 const float *rec = sm.rec[rslot];
                 float cx, cy, cz;
                 member_coords(rec, cx, cy, cz);
                 float *const ab = acts_of(m);
-                const int tr0 = warp == 0 ? 0 : 32;
-                const bool trw = warp == 0 || warp == 13;
                 TRACE_EVT(trw, m, tr0 + 0);
 
                 // ---------------- layer 0 on CUDA cores -> A operand of layer 1 (units 0-5 normally exist already)

@@ -20,7 +20,7 @@ from conftest import MAXI, MINI, make_ensemble, sample_latent       # noqa: E402
 from nphm_b200 import _native                                       # noqa: E402
 
 EP = ['iter start', 'E0b done', 'E3b(prev)+blend done', 'M1 done seen', 'E1 done', 'M2 done seen', 'E2 done',
-      'waiting for M3', 'M3 done seen', 'E3a done', 'E0a(next) done']
+      'waiting for M3', 'M3 done seen', 'E3a done', 'E0a(next) done', 'loop top (before the record wait)']
 IS = {16: 'M1 may start', 17: 'M1 S k-steps issued', 18: 'M1 all issued', 19: 'a1[0] seen', 20: 'a1[1] seen',
       22: 'M2 all issued', 23: 'a2[0] seen', 24: 'a2[1] seen', 25: 'a2[2] seen', 26: 'a2[3] seen', 28: 'M3 all issued'}
 
