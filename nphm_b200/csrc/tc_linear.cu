@@ -82,6 +82,9 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16])
                  : "r"(taddr) : "memory");
 }
 
+// MODE and PACKED_C (packed output present) are compile-time: the epilogue is the longest part of a latency-bound layer and
+// loses ~a fifth of its instructions when the per-unit mode / layout tests disappear
+template <int MODE, bool PACKED_C>
 __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
     // MULT epilogue with a blocked multiplier and packed A (the fp32 staging ring of A is idle then): the producer streams the
     // multiplier, unit by unit (16 features x 128 rows = 8 KB contiguous), into that ring while the MMAs run - read from global
     // memory inside the epilogue, every unit cost a full memory round trip (measured: 5 k cycles per unit)
-    const bool mul_ring = p.Ap && p.mode == kModeMult && p.Mul && (p.blocked || p.mul_blocked) && p.mul_div == 1;
+    const bool mul_ring = p.Ap && MODE == kModeMult && p.Mul && (p.blocked || p.mul_blocked) && p.mul_div == 1;
     const int n_units = p.Nt / 16;
     float (*mring)[16][128] = reinterpret_cast<float (*)[16][128]>(a32);
     auto unit_in_ring = [&](int u) { return mul_ring && n0 + 16 * u + 16 <= p.ldmul; };     // whole unit inside the tile's block
@@ -279,13 +282,13 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                                      : p.Mul + (size_t)z * p.sMul + (size_t)mrow * p.ldmul;
         const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + (size_t)z * p.sRow + row) : 1.0f;
         float *const Cz = p.C ? p.C + (size_t)z * p.sC : nullptr;
-        uint8_t *const cp = p.Cp ? p.Cp + (size_t)z * p.sCp + (size_t)blockIdx.x * p.c_tile_steps * kPackedStep +
+        uint8_t *const cp = PACKED_C ? p.Cp + (size_t)z * p.sCp + (size_t)blockIdx.x * p.c_tile_steps * kPackedStep +
                                        (size_t)(t >> 3) * 256 + (size_t)(t & 7) * 16 : nullptr;
         const float *app = (p.app && row_ok) ? p.app + (size_t)row * p.app_ld : nullptr;       // appended input columns (skip connection)
         const int app_hot = p.app_onehot ? (int)(row % p.app_w) : -1;
-        const bool aux_blk = p.mode == kModeMult ? mul_blk : false;
-        const float *aux_src = p.mode == kModeMult ? mul : bias;      // bias (LINEAR / SOFTPLUS) or multiplier (MULT)
-        const int aux_ld = p.mode == kModeMult ? p.ldmul : p.ldb;
+        const bool aux_blk = MODE == kModeMult ? mul_blk : false;
+        const float *aux_src = MODE == kModeMult ? mul : bias;        // bias (LINEAR / SOFTPLUS) or multiplier (MULT)
+        const int aux_ld = MODE == kModeMult ? p.ldmul : p.ldb;
         const bool aux_vec = aux_src && (aux_ld % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(aux_src) & 15) == 0);
         const bool c_vec = (p.ldc % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
         const bool d_vec = p.Dv && (p.lddv % 4 == 0) && ((n0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Dv) & 15) == 0);
@@ -335,10 +338,10 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                     if (a < p.app_w) x = p.app_onehot ? (a == app_hot ? 1.f : 0.f) : (app ? app[a] : 0.f);
                 }
                 if (FULL || n0 + c0 + e < p.N) {
-                    if (p.mode == kModeMult) x *= aux[e] * rscale;
+                    if (MODE == kModeMult) x *= aux[e] * rscale;
                     else {
                         x += aux[e];
-                        if (p.mode == kModeSoftplus) {
+                        if (MODE == kModeSoftplus) {
                             // softplus(beta = 100) and its derivative in log2 units: u = 100 log2(e) x
                             // log2(1 + 2^-|u|) by a degree-6 polynomial in 2^-|u| on the FMA pipe (the fused kernels' scheme) on
                             // every other element, by the second MUFU on the rest: the pass is bound by the MUFU pipe
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tc_kernel(const LinearPara
                 o[e] = x;
             }
             TCL_EVT(threadIdx.x == 0, 13, c0 >> 4);
-            if (cp && ((n0 + c0) >> 4) < p.c_ksteps) {
+            if (PACKED_C && ((n0 + c0) >> 4) < p.c_ksteps) {
                 // operand-ready output: this unit is k-step (n0 + c0) / 16 of the next layer's A tile, fp16 hi | lo, core-matrix order
                 uint32_t hi[8], lo[8];
 #pragma unroll
@@ -520,10 +523,14 @@ int launch_linear(const PackedLinear &w, LinearParams p, cudaStream_t stream)
     p.stages = kMaxStages;
     if (many && smem_bytes(p.Nt, kMaxStages, packed_a) > 112 * 1024 && smem_bytes(p.Nt, 3, packed_a) <= 112 * 1024) p.stages = 3;
     const int smem = smem_bytes(p.Nt, p.stages, packed_a);
-    NPHM_CUDA_CHECK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes(kMaxNt, kMaxStages, false)));
+    using Kernel = void (*)(const LinearParams);
+    const bool pc = p.Cp != nullptr;
+    Kernel kern = p.mode == kModeMult       ? (pc ? (Kernel)linear_tc_kernel<kModeMult, true> : (Kernel)linear_tc_kernel<kModeMult, false>)
+                  : p.mode == kModeSoftplus ? (pc ? (Kernel)linear_tc_kernel<kModeSoftplus, true> : (Kernel)linear_tc_kernel<kModeSoftplus, false>)
+                                            : (pc ? (Kernel)linear_tc_kernel<kModeLinear, true> : (Kernel)linear_tc_kernel<kModeLinear, false>);
+    NPHM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(kMaxNt, kMaxStages, false)));
     dim3 grid((unsigned)ceil_div(p.M, 128), (unsigned)w.n_tiles, (unsigned)p.batch);
-    linear_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+    kern<<<grid, kThreads, smem, stream>>>(p);
     NPHM_CUDA_CHECK(cudaGetLastError());
     return NPHM_OK;
 }
